@@ -1,0 +1,159 @@
+/*
+ * hmp_device.h -- device-side data layout shared by the host code (hmp_api.cu) and the kernels
+ * (hmp_kernels.cu). Everything here is plain-old-data that is memcpy'd to the GPU.
+ *
+ * Coordinates: the host translates the scene into a robot-centred frame (origin = robot position at
+ * t = 0, NO rotation) before narrowing to FP32, so FP32 magnitudes stay below the costmap half-width
+ * no matter where in the map frame the robot is. The absolute pose is carried in FP64 beside it for
+ * costmap / MapGrid cell indexing (reference: costmap_2d::Costmap2D::worldToMap).
+ */
+#ifndef HMP_DEVICE_H_
+#define HMP_DEVICE_H_
+
+#include <stdint.h>
+
+#include "../../include/hmp_planner.h"
+
+#define HMP_DEV_MAX_KERNEL_PTS 9   /* centre + 8 offsets (RECTANGLE kernel) */
+
+/* Rollout-invariant record of one object treated with the STATIC interaction formulation
+ * (reference StaticObject, world.h:24-41). d0 = object point - robot-side point at t = 0; during the
+ * rollout dist_v = d0 - (c - c0) because World::predict only translates the robot-side point with the
+ * centroid (world.cpp:107-110). */
+struct DevStatic {
+	float d0x, d0y;
+};
+
+/* One object treated with the DYNAMIC formulation (DynamicObject, world.h:43-59). */
+struct DevDynamic {
+	float d0x, d0y;   /* object point - robot-side point at t = 0                     */
+	float vx, vy;     /* object velocity (global)                                     */
+	float psi0;       /* yaw of the robot-side closest-point pose at t = 0            */
+	float dir_beta;   /* wrap(direction(vel)), world.cpp:183                          */
+	float speed;      /* |vel_xy|, world.cpp:180-181                                  */
+	float _pad;
+};
+
+/* humap_local_planner::Person prediction source (person.h, trajectory.h:160-193) + covariances +
+ * the speed-dependent personal-space variances (personal_space_intrusion_cost_function.cpp:55-58). */
+struct DevPerson {
+	float x, y, yaw, _p0;      /* pose at t = 0, robot-centred frame */
+	float vx, vy, vth, _p1;
+	float cxx, cxy, cyx, cyy;
+	float var_front, var_rear, var_side, _p2;
+};
+
+/* Group: static over the horizon (group.h:18-21) so the inverse covariance of the O-space Gaussian
+ * (fformation_space_intrusion_cost_function.cpp:60-61 + pose covariance) is precomputed on the host:
+ * q = ia dx^2 + 2 ib dx dy + ic dy^2, cost = exp(-q / 2). */
+struct DevGroup {
+	float x, y, ia, ib;
+	float ic, _p0, _p1, _p2;
+};
+
+/* Per-scene header. Arrays follow in one blob; offsets are in bytes from the blob start. */
+struct DevScene {
+	double x0, y0, yaw0;          /* robot pose at t = 0 (absolute, map frame)                         */
+	float u0x, u0y, u0w;          /* robot global velocity at t = 0 (computeVelocityGlobal(vel_, pose_)) */
+	float vlx, vly, vlw;          /* vel_: current base-frame velocity (smoothness critics)            */
+	float glx, gly;               /* goal_local_ - (x0, y0)                                            */
+	float gx, gy;                 /* goal_       - (x0, y0)                                            */
+	int32_t n_static0;            /* objects static at step 0                                          */
+	int32_t n_static;             /* ... from step 1 on (adds objects re-classified by World::predict, App. A #5) */
+	int32_t n_dynamic;            /* objects dynamic at step 0                                         */
+	int32_t n_dynamic_later;      /* ... from step 1 on (prefix of the dynamic array)                  */
+	int32_t n_people, n_groups;
+	uint32_t off_static, off_dynamic, off_people, off_groups;
+	uint32_t blob_bytes;          /* header + arrays, multiple of 16                                   */
+	int32_t _pad;
+	double hv_prev[HMP_NUM_MAPGRIDS];   /* highest_valid_cost_prev_ per MapGrid critic                    */
+};
+
+/* Flattened HumapConfig for the device: FP32 where the arithmetic is FP32, FP64 where the reference's
+ * doubles decide an integer (cell index) or the final weighted sum. */
+struct DevParams {
+	/* --- time discretisation (social_trajectory_generator.cpp:324-328) */
+	int32_t T;                    /* num_steps                                      */
+	int32_t n_ttc_extra;          /* iterations of the TTC look-ahead loop (ttc_cost_function.cpp:100) */
+	double dt_d;                  /* sim_time / T                                   */
+	float dt;
+	float people_dt;
+	/* --- limits */
+	float max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_vel_theta, min_vel_theta;
+	float max_vel_trans, min_vel_trans;
+	float acc_x, acc_y, acc_th, acc_decel;     /* acc_decel = hypot(acc_x, acc_y)  */
+	float rot_comp;
+	float back_max;               /* (min_vel_x < 0) ? |min_vel_x| : 0              */
+	int32_t maintain_rate;
+	/* --- SFM */
+	int32_t fov_method, filter_forces, disable_interaction;
+	float mass, m_over_tau;
+	float k_int, k_stat, k_dyn, min_force, max_force;
+	float fov_sigma;              /* Gaussian sigma = cfg.fov (variance (2 fov / 2)^2) */
+	float fov_gauss_scale;        /* 1 / (sigma sqrt(2 pi))                            */
+	float fov_neg_inv_2var;       /* -1 / (2 sigma^2)                                  */
+	float base[9];                /* (float)cfg.{speed_desired, an, bn, cn, ap, bp, cp, aw, bw}: SFM float members */
+	/* --- FIS */
+	int32_t fis_on, fis_fov_method;
+	float fis_force_factor, fis_range;
+	float fis_fov_half;           /* linear method: cfg.fov / 2                        */
+	float fis_gauss_scale, fis_neg_inv_2var;
+	/* --- candidates */
+	int32_t amp_n[HMP_NUM_AMPLIFIERS];
+	int32_t n_grid;               /* product of amp_n                                  */
+	int32_t n_candidates;         /* n_grid + n_extra                                  */
+	/* --- costmap geometry */
+	int32_t size_x, size_y;
+	double origin_x, origin_y, resolution, inv_resolution;
+	/* --- critics */
+	double scale[HMP_NUM_COSTS];
+	int32_t n_footprint;
+	int32_t n_kernel_pts;         /* 1, 5 (CROSS) or 9 (RECTANGLE)                     */
+	double kernel_dx[HMP_DEV_MAX_KERNEL_PTS];   /* offset of placement k in the robot frame: sep * (cos a_k, sin a_k) */
+	double kernel_dy[HMP_DEV_MAX_KERNEL_PTS];
+	double footprint_x[HMP_MAX_FOOTPRINT];
+	double footprint_y[HMP_MAX_FOOTPRINT];
+	int32_t occdist_sum;
+	int32_t mg_stop_on_failure[HMP_NUM_MAPGRIDS];
+	int32_t mg_kernel[HMP_NUM_MAPGRIDS];
+	int32_t _padc;
+	double mg_xshift[HMP_NUM_MAPGRIDS], mg_yshift[HMP_NUM_MAPGRIDS], mg_mult[HMP_NUM_MAPGRIDS];
+	float unsat_max_trans, unsat_max_x, unsat_max_y;
+	float backward_penalty;
+	float ttc_collision_distance, ttc_rollout_time;
+	float hd_person_radius, hd_neg_inv_2var_fov, hd_dmin, hd_inv_max_speed;
+	float ps_min_dist, ps_inv_max_speed;
+	int32_t unsat_whole, hd_whole, psi_whole, fsi_whole, ps_whole;
+	int32_t _pade;
+};
+
+/* Kernel argument block (passed by value). */
+struct KernelArgs {
+	const DevParams* params;         /* device */
+	const double* amp_values;        /* [10][HMP_MAX_AMP_VALUES] device                           */
+	const double* extra_samples;     /* [n_extra][10] device, or null                             */
+	const uint8_t* scenes;           /* n_scenes blobs, stride scene_stride bytes                  */
+	uint32_t scene_stride;
+	int32_t n_scenes;
+	const uint8_t* costmaps;         /* n_scenes costmaps, stride costmap_stride bytes (mult of 16) */
+	uint32_t costmap_stride;
+	int32_t costmap_in_smem;
+	const float* mapgrids;           /* [n_scenes][4][size_y * size_x]                            */
+	const float* fis_table;          /* [100][12]: x_i, mu_k(x_i) k = 0..10                       */
+	/* selection */
+	const int32_t* cand_list;        /* explicit candidate indices (detail mode) or null          */
+	int32_t n_work;                  /* candidates per scene to evaluate                          */
+	int32_t _pad;
+	double* totals;                  /* [n_scenes][n_candidates] or null                          */
+	unsigned long long* block_best;  /* scratch [n_scenes][gridDim.x] x 2 (cost bits, index)      */
+	unsigned int* counters;          /* [n_scenes][4]: ticket, n_generated, n_valid, pad          */
+	float* hv_out;                   /* [n_scenes][4] highest_valid_cost (float bits, atomicMax)  */
+	double* best_out;                /* [n_scenes][2]: best total, best index (as double)         */
+	/* detail outputs (DETAIL kernel only) */
+	double* d_costs;                 /* [n_work][14]                                               */
+	double* d_seeds;                 /* [n_work][3]                                                */
+	double* d_poses;                 /* [n_work][T][3]                                             */
+	double* d_forces;                /* [n_work][T][8] or null                                     */
+};
+
+#endif

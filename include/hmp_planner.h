@@ -1,0 +1,323 @@
+/*
+ * hmp_planner.h -- C ABI of the B200-native trajectory sampling + scoring hot path.
+ *
+ * This is the drop-in boundary for ONE path of rayvburn/humap_local_planner: the call
+ *     scored_sampling_planner_.findBestTrajectory(result_traj_, &traj_explored_)
+ * at reference src/humap_planner.cpp:1367, i.e. SocialTrajectoryGenerator rollouts
+ * (src/social_trajectory_generator.cpp:292-462) -> 14 TrajectoryCostFunction critics
+ * (src/humap_planner.cpp:68-82) -> weighted total -> first strict minimum.
+ *
+ * Conventions (mirroring the reference):
+ *  - plain C, plain pointers and sizes, no ownership transfer: every pointer argument is a
+ *    caller-owned HOST buffer that is only read (or written, for outputs) during the call;
+ *  - every function returns an int status: 0 ok, < 0 error (HMP_E_*); nothing throws;
+ *  - one context per host thread and per GPU; a context is not re-entrant (the reference holds
+ *    cfg_->getMutex() for the whole cycle, src/humap_planner.cpp:357);
+ *  - negative COSTS are the reference's "invalid trajectory" codes and are preserved:
+ *      -1  generator rejected the sample (velocity limits), social_trajectory_generator.cpp:319,411
+ *      -4  MapGrid point off the map, map_grid_cost_function.cpp:166-170
+ *      -6  footprint touches lethal / unknown / leaves the map, obstacle_separation_cost_function.cpp:225
+ *      -7  trajectory centre off the map, obstacle_separation_cost_function.cpp:231
+ *      -9  empty footprint, obstacle_separation_cost_function.cpp:92
+ *      -10 / -12 TTC preconditions, ttc_cost_function.cpp:32,38
+ *  - there is NO CPU fallback behind this ABI: if no CUDA device / kernel image is usable the
+ *    calls fail with HMP_E_CUDA.
+ */
+#ifndef HMP_PLANNER_H_
+#define HMP_PLANNER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMP_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define HMP_OK            0
+#define HMP_E_INVALID    -1   /* bad argument (null pointer, negative size, inconsistent sizes) */
+#define HMP_E_CUDA       -2   /* CUDA runtime error or no usable device; see hmp_last_error()  */
+#define HMP_E_NOT_READY  -3   /* a required hmp_set_* call is missing                           */
+#define HMP_E_CAPACITY   -4   /* problem does not fit the configured limits (see HMP_MAX_*)     */
+
+/* ---- compile-time limits ------------------------------------------------------------------ */
+#define HMP_NUM_AMPLIFIERS      10     /* SampleAmplifierSet, social_trajectory_generator.h:28-52 */
+#define HMP_MAX_AMP_VALUES      64     /* values per amplifier axis                                */
+#define HMP_NUM_COSTS           14     /* critics, humap_planner.cpp:68-82                          */
+#define HMP_NUM_MAPGRIDS        4
+#define HMP_MAX_FOOTPRINT       64     /* footprint polygon vertices                                */
+#define HMP_MAX_STEPS           512    /* rollout steps per candidate                               */
+
+/* Critic order == evaluation order of the reference (src/humap_planner.cpp:68-82). */
+enum HmpCostIndex {
+	HMP_COST_OBSTACLE = 0,        /* ObstacleSeparationCostFunction           */
+	HMP_COST_PATH = 1,            /* MapGridCostFunction path_costs_          */
+	HMP_COST_GOAL = 2,            /* MapGridCostFunction goal_costs_          */
+	HMP_COST_ALIGNMENT = 3,       /* MapGridCostFunction alignment_costs_     */
+	HMP_COST_GOAL_FRONT = 4,      /* MapGridCostFunction goal_front_costs_    */
+	HMP_COST_UNSATURATED = 5,     /* UnsaturatedTranslationCostFunction       */
+	HMP_COST_BACKWARD = 6,        /* base_local_planner::PreferForwardCostFunction */
+	HMP_COST_TTC = 7,             /* TTCCostFunction                          */
+	HMP_COST_HEADING_CHANGE = 8,  /* HeadingChangeSmoothnessCostFunction      */
+	HMP_COST_VEL_SMOOTHNESS = 9,  /* VelocitySmoothnessCostFunction           */
+	HMP_COST_HEADING_DIST = 10,   /* HeadingDisturbanceCostFunction           */
+	HMP_COST_PERSONAL_SPACE = 11, /* PersonalSpaceIntrusionCostFunction       */
+	HMP_COST_FFORMATION = 12,     /* FformationSpaceIntrusionCostFunction     */
+	HMP_COST_PASSING_SPEED = 13   /* PassingSpeedCostFunction                 */
+};
+
+/* Order of the MapGrid slots used by hmp_set_mapgrid. */
+enum HmpMapGridIndex {
+	HMP_GRID_PATH = 0,
+	HMP_GRID_GOAL = 1,
+	HMP_GRID_ALIGNMENT = 2,
+	HMP_GRID_GOAL_FRONT = 3
+};
+
+/* Order of the amplifier axes == nesting order of the 10 loops, outermost first
+ * (src/social_trajectory_generator.cpp:166-175). Candidate index c decodes as a mixed-radix
+ * number with HMP_AMP_SPEED the most significant digit and HMP_AMP_AS the least significant. */
+enum HmpAmplifierIndex {
+	HMP_AMP_SPEED = 0, HMP_AMP_AN = 1, HMP_AMP_BN = 2, HMP_AMP_CN = 3, HMP_AMP_AP = 4,
+	HMP_AMP_BP = 5, HMP_AMP_CP = 6, HMP_AMP_AW = 7, HMP_AMP_BW = 8, HMP_AMP_AS = 9
+};
+
+/* ---- parameters (flattened HumapConfig, include/humap_local_planner/humap_config.h) -------- */
+
+/* PlannerLimitsParams (humap_config.h:13-24) + base_local_planner::LocalPlannerLimits fields used on the path */
+typedef struct HmpLimits {
+	double max_vel_trans, min_vel_trans;
+	double max_vel_x, min_vel_x;
+	double max_vel_y, min_vel_y;
+	double max_vel_theta, min_vel_theta;
+	double acc_lim_x, acc_lim_y, acc_lim_theta;
+	double twist_rotation_compensation;
+	int32_t maintain_vel_components_rate;
+	int32_t _pad;
+} HmpLimits;
+
+/* GeneralParams subset (humap_config.h:26-58) */
+typedef struct HmpGeneral {
+	double sim_time;
+	double sim_granularity;
+	double angular_sim_granularity;
+	double sim_period;
+	/* dt of the constant-velocity people/group predictions (humap_planner_ros.cpp:530): the
+	 * reference uses sim_granularity; kept separate because the robot uses sim_time / steps. */
+	double people_prediction_dt;
+	int32_t discretize_by_time;   /* planMovingRobot passes true (humap_planner.cpp:1313) */
+	int32_t _pad;
+} HmpGeneral;
+
+/* SfmParams (humap_config.h:78-130). Equation parameters are doubles here; they are truncated to
+ * float after multiplication by the amplifier exactly where the reference does it
+ * (sfm/social_force_model.h:422-446 float members, social_trajectory_generator.cpp:627-637). */
+typedef struct HmpSfm {
+	double fov;                   /* HALF of the robot's field of view */
+	double mass;
+	double internal_force_factor;
+	double static_interaction_force_factor;
+	double dynamic_interaction_force_factor;
+	double min_force, max_force;
+	double speed_desired, relaxation_time;
+	double an, bn, cn, ap, bp, cp, aw, bw;
+	int32_t fov_factor_method;    /* 0 Gaussian, 1 linear (sfm::FovCalculationMethod) */
+	int32_t filter_forces;
+	int32_t disable_interaction_forces;
+	int32_t _pad;
+} HmpSfm;
+
+/* FisParams (humap_config.h:137-152). `as` is not here: the reference never reads it. */
+typedef struct HmpFis {
+	double force_factor;          /* <= 0 disables the fuzzy human-action force (social_conductor.cpp:30-35) */
+	double human_action_range;
+	double fov;                   /* passed as the FULL fov argument of computeFactorFOV (social_conductor.cpp:181-190) */
+	int32_t fov_factor_method;    /* 0 Gaussian, 1 linear, other: factor 1.0 */
+	int32_t _pad;
+} HmpFis;
+
+/* CostParams (humap_config.h:226-287) + the per-cycle values HumapPlanner pushes into its critics
+ * (updateCostParameters humap_planner.cpp:868-928, updateLocalCosts :1054-1141). */
+typedef struct HmpCosts {
+	/* Effective scale of every critic as returned by getScale() when findBestTrajectory is
+	 * entered (MapGrid scales already multiplied by the costmap resolution, dynamic per-cycle
+	 * scales already applied). A zero scale skips the critic (SimpleScoredSamplingPlanner). */
+	double scale[HMP_NUM_COSTS];
+	/* ObstacleSeparationCostFunction */
+	double occdist_separation;
+	int32_t occdist_separation_kernel;   /* 0 CROSS, 1 RECTANGLE, else none */
+	int32_t occdist_sum_scores;
+	/* MapGridCostFunction x4, slots HmpMapGridIndex */
+	double xshift[HMP_NUM_MAPGRIDS];
+	double yshift[HMP_NUM_MAPGRIDS];
+	int32_t stop_on_failure[HMP_NUM_MAPGRIDS];
+	/* customised MapGrid heuristic (map_grid_cost_function.h: n_kernel_size_, n_cost_multiplier_);
+	 * applies to HMP_GRID_ALIGNMENT and HMP_GRID_GOAL_FRONT only (the humap_local_planner class);
+	 * path/goal use the upstream base_local_planner class. */
+	int32_t neighbour_kernel_size[HMP_NUM_MAPGRIDS];
+	double neighbour_cost_multiplier[HMP_NUM_MAPGRIDS];
+	/* UnsaturatedTranslationCostFunction::setParameters */
+	double unsat_max_trans_vel, unsat_max_vel_x, unsat_max_vel_y;
+	/* PreferForwardCostFunction */
+	double backward_penalty;
+	/* TTCCostFunction::setParameters */
+	double ttc_rollout_time, ttc_collision_distance;
+	/* HeadingDisturbanceCostFunction::setParameters */
+	double hd_fov_person;          /* FULL fov (2 * person_fov) */
+	double hd_person_model_radius;
+	double hd_robot_circumradius;
+	double hd_max_speed;
+	/* PassingSpeedCostFunction::setParameters */
+	double ps_max_speed, ps_min_dist;
+	int32_t unsat_whole_horizon;
+	int32_t hd_whole_horizon;
+	int32_t psi_whole_horizon;
+	int32_t fsi_whole_horizon;
+	int32_t ps_whole_horizon;
+	int32_t _pad;
+} HmpCosts;
+
+typedef struct HmpParams {
+	HmpLimits limits;
+	HmpGeneral general;
+	HmpSfm sfm;
+	HmpFis fis;
+	HmpCosts costs;
+} HmpParams;
+
+/* ---- per-cycle scene ---------------------------------------------------------------------- */
+
+/* One World::addObstacle() call (src/world.cpp:43-63): closest-point pair + object velocity. */
+typedef struct HmpObstacle {
+	double robot_x, robot_y, robot_yaw;   /* pose of the robot-footprint point closest to the object */
+	double obj_x, obj_y, obj_yaw;         /* pose of the object point closest to the robot          */
+	double vx, vy, vth;                   /* object velocity, global frame                           */
+	int32_t force_dynamic;                /* addObstacle(..., force_dynamic_type)                    */
+	int32_t _pad;
+} HmpObstacle;
+
+/* humap_local_planner::Person = people_msgs_utils::Person + constant-velocity prediction (person.h) */
+typedef struct HmpPerson {
+	double x, y, yaw;
+	double vx, vy, vth;
+	double cov_xx, cov_xy, cov_yx, cov_yy;
+} HmpPerson;
+
+/* humap_local_planner::Group (group.h); groups are static over the horizon (group.h:18-21) */
+typedef struct HmpGroup {
+	double x, y, yaw;
+	double span_x, span_y;
+	double cov_xx, cov_xy, cov_yy;
+} HmpGroup;
+
+typedef struct HmpWorld {
+	double robot_x, robot_y, robot_yaw;   /* pose_ (humap_planner.cpp:369)                     */
+	double vel_x, vel_y, vel_th;          /* vel_: current BASE-frame velocity (:360)          */
+	double goal_local_x, goal_local_y, goal_local_yaw;   /* goal_local_                         */
+	double goal_x, goal_y, goal_yaw;      /* goal_                                              */
+	const HmpObstacle* obstacles;         /* in World::addObstacle call order                   */
+	const HmpPerson* people;              /* people_env_model_                                  */
+	const HmpGroup* groups;               /* groups_env_model_                                  */
+	int32_t n_obstacles, n_people, n_groups;
+	int32_t _pad;
+} HmpWorld;
+
+/* TrajectorySamplingParams (humap_config.h:176-224): per axis {min, max, granularity}. */
+typedef struct HmpSampling {
+	double amp_min[HMP_NUM_AMPLIFIERS];
+	double amp_max[HMP_NUM_AMPLIFIERS];
+	double amp_granularity[HMP_NUM_AMPLIFIERS];
+} HmpSampling;
+
+/* Explicit sample, appended after the grid (initialise(..., additional_samples, ...),
+ * social_trajectory_generator.cpp:51-70). Axis order HmpAmplifierIndex. */
+typedef struct HmpSample {
+	double amp[HMP_NUM_AMPLIFIERS];
+} HmpSample;
+
+/* ---- result ------------------------------------------------------------------------------- */
+typedef struct HmpResult {
+	int32_t status;                /* 0: a valid trajectory was found; 1: none valid (cost < 0)   */
+	int32_t best_index;            /* index into the generator's sample list; -1 if none          */
+	int32_t n_candidates;          /* samples in the list                                          */
+	int32_t n_generated;           /* nextTrajectory() returned true                               */
+	int32_t n_valid;               /* total cost >= 0                                              */
+	int32_t n_poses;               /* poses of the winner written to `poses`                       */
+	double best_total;             /* result_traj_.cost_ (weighted); -7 if none (humap_planner.cpp:1364) */
+	double costs[HMP_NUM_COSTS];   /* RAW (unscaled) critic outputs of the winner, NaN if the critic was skipped */
+	double xv, yv, thetav;         /* seed twist = twist of step 0 (social_trajectory_generator.cpp:415-419)   */
+	double time_delta;             /* traj.time_delta_                                                         */
+	double amplifiers[HMP_NUM_AMPLIFIERS];  /* the winner's SampleAmplifierSet                                */
+	double highest_valid_cost[HMP_NUM_MAPGRIDS];  /* highest_valid_cost_ after the cycle (map_grid_cost_function.cpp:87,135) */
+	double gpu_ms;                 /* device time of the cycle (CUDA events), milliseconds                       */
+} HmpResult;
+
+typedef struct HmpContext HmpContext;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+/* Creates a context bound to CUDA device `device_id`. Returns NULL on failure (hmp_last_error()). */
+HmpContext* hmp_create(int device_id);
+void hmp_destroy(HmpContext* ctx);
+/* Text of the last error on this thread (never NULL). */
+const char* hmp_last_error(void);
+int hmp_abi_version(void);
+
+/* ---- configuration: replaces HumapPlanner::reconfigure -> generator_social_.setParameters +
+ *      updateCostParameters (humap_planner.cpp:177-226, :868-928) and the per-cycle setScale /
+ *      setXShift calls of updateLocalCosts (:1054-1141) ----------------------------------------- */
+int hmp_set_params(HmpContext* ctx, const HmpParams* params);
+
+/* Replaces the costmap_2d::Costmap2D* every critic holds (row-major, index = my * size_x + mx). */
+int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y,
+                    double origin_x, double origin_y, double resolution);
+
+/* Replaces MapGridCostFunction::prepare() output (map_grid_cost_function.cpp:67-79): the wave-front
+ * grid map_(x, y).target_dist of slot `grid`, row-major, size_x * size_y doubles, together with
+ * highest_valid_cost_prev_ of that critic. Values are integers < 2^24 (cell counts, obstacleCosts(),
+ * unreachableCellCosts()), which is checked. */
+int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, double highest_valid_cost_prev);
+
+/* Replaces ObstacleSeparationCostFunction::setFootprint (humap_planner.cpp:1059); xy interleaved. */
+int hmp_set_footprint(HmpContext* ctx, const double* xy, int32_t n_points);
+
+/* ---- the hot path: replaces generator_social_.initialise(...) (humap_planner.cpp:1307-1314) +
+ *      scored_sampling_planner_.findBestTrajectory(...) (:1367) for the social generator.
+ *      `extra`/`n_extra` may be NULL/0. `poses_out` (3 doubles per pose: x, y, yaw) may be NULL;
+ *      at most poses_capacity poses are written. ------------------------------------------------ */
+int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling,
+             const HmpSample* extra, int32_t n_extra,
+             HmpResult* result, double* poses_out, int32_t poses_capacity);
+
+/* Same, for a batch of independent scenes that share params, costmap geometry and sampling but
+ * have their own world, costmap cells and MapGrids (BASELINE config "batched scenes"). Scene s uses
+ * worlds[s], cells + s * size_x * size_y, target_dist[g] + s * size_x * size_y. One launch. */
+int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes,
+                   const uint8_t* cells, const double* const target_dist[HMP_NUM_MAPGRIDS],
+                   const double* highest_valid_cost_prev /* [n_scenes][4] or NULL */,
+                   const HmpSampling* sampling, HmpResult* results);
+
+/* ---- diagnostics of the LAST hmp_plan (traj_explored_, humap_planner.cpp:1367,1969-2084) ------ */
+/* Weighted total per candidate (negative = reference error code); n must equal n_candidates. */
+int hmp_get_explored_totals(HmpContext* ctx, double* totals, int32_t n);
+/* Re-runs the given candidates with full write-back: raw per-critic costs [n][HMP_NUM_COSTS]
+ * (NaN where the reference would not have evaluated the critic), seed twist [n][3], and the poses
+ * [n][n_steps][3]. Any output pointer may be NULL. Used by the parity tests and by the adapter for
+ * traj_explored_. */
+int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n,
+                double* costs_out, double* seeds_out, double* poses_out, int32_t* n_steps_out);
+
+/* ---- device-side helpers exposed for bit-exact parity tests (no reference counterpart) -------- */
+/* costmap_2d::Costmap2D::worldToMap on the device for n points; ok[i] = 0/1. */
+int hmp_debug_world_to_map(HmpContext* ctx, const double* wx, const double* wy, int32_t n,
+                           int32_t* mx, int32_t* my, int32_t* ok);
+/* CostmapModel::footprintCost on the device for n poses (x, y, yaw) with the configured footprint. */
+int hmp_debug_footprint_cost(HmpContext* ctx, const double* xyt, int32_t n, double* cost);
+
+/* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
+int64_t hmp_launch_count(HmpContext* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMP_PLANNER_H_ */

@@ -1,0 +1,63 @@
+/*
+ * hmp_oracle.h -- C interface of the CPU oracle (see hmp_oracle.cpp). TEST INFRASTRUCTURE ONLY:
+ * nothing under humap_local_planner_b200/ may include, link or load this.
+ */
+#ifndef HMP_ORACLE_H_
+#define HMP_ORACLE_H_
+
+#include "../include/hmp_planner.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcPlanInput {
+	const HmpParams* params;
+	const HmpWorld* world;
+	const HmpSampling* sampling;
+	const HmpSample* extra;
+	int32_t n_extra;
+	/* costmap */
+	int32_t size_x, size_y;
+	const uint8_t* cells;
+	double origin_x, origin_y, resolution;
+	/* MapGridCostFunction::prepare() outputs */
+	const double* target_dist[HMP_NUM_MAPGRIDS];
+	double highest_valid_cost_prev[HMP_NUM_MAPGRIDS];
+	/* footprint */
+	const double* footprint_xy;
+	int32_t n_footprint;
+	/* 1: reference semantics (SimpleScoredSamplingPlanner stops summing once worse than the best);
+	 * 0: full totals for every candidate (what the GPU path reports in hmp_get_explored_totals) */
+	int32_t early_exit;
+	/* candidate sub-range [cand_begin, cand_end) to evaluate; cand_end <= 0 means all (used by the
+	 * multi-threaded CPU baseline) */
+	int32_t cand_begin, cand_end;
+} OrcPlanInput;
+
+typedef struct OrcPlanOutput {
+	HmpResult result;
+	/* all optional (NULL to skip); C = number of candidates, T = number of steps */
+	double* totals;      /* [C] weighted total or negative code (-1 = generator rejected)       */
+	double* costs;       /* [C][HMP_NUM_COSTS] raw critic outputs, NaN = not evaluated           */
+	double* seeds;       /* [C][3]                                                               */
+	double* poses;       /* [C][T][3]                                                            */
+	int32_t* n_poses;    /* [C]                                                                  */
+	int32_t* generated;  /* [C]                                                                  */
+	double* best_poses;  /* [T][3]                                                               */
+	double* forces;      /* [T][8] per-step forces of candidate `forces_candidate`               */
+	int32_t forces_candidate;
+	int32_t _pad;
+} OrcPlanOutput;
+
+int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out);
+int orc_num_candidates(const HmpSampling* sampling, int n_extra);
+int orc_num_steps(const HmpParams* P, const HmpWorld* w);
+int orc_samples(const HmpSampling* sampling, const HmpSample* extra, int n_extra, HmpSample* out);
+void orc_mapgrid_compute(const uint8_t* cells, int size_x, int size_y, double origin_x, double origin_y,
+                         double resolution, const double* plan_xy, int n_plan, int local_goal, double* target_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
