@@ -1,0 +1,327 @@
+"""ctypes binding of the C ABI in include/hmp_planner.h (the drop-in boundary of the sampling + scoring path).
+
+The structures mirror the header field by field; `Planner` is a thin convenience wrapper over the
+`hmp_*` entry points used by tests/ and bench.py. The library is CUDA-only: loading fails loudly
+if the shared object is missing and `Planner()` raises if no sm_100 device is usable. There is no
+CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+NUM_AMPLIFIERS = 10
+MAX_AMP_VALUES = 64
+NUM_COSTS = 14
+NUM_MAPGRIDS = 4
+MAX_FOOTPRINT = 64
+MAX_STEPS = 512
+
+COST_NAMES = (
+    "obstacle", "path", "goal", "alignment", "goal_front", "unsaturated", "backward", "ttc",
+    "heading_change", "vel_smoothness", "heading_dist", "personal_space", "fformation", "passing_speed",
+)
+AMP_NAMES = ("speed", "an", "bn", "cn", "ap", "bp", "cp", "aw", "bw", "as")
+
+HMP_OK, HMP_E_INVALID, HMP_E_CUDA, HMP_E_NOT_READY, HMP_E_CAPACITY = 0, -1, -2, -3, -4
+
+_d, _i = C.c_double, C.c_int32
+
+
+class HmpLimits(C.Structure):
+    _fields_ = [(n, _d) for n in (
+        "max_vel_trans", "min_vel_trans", "max_vel_x", "min_vel_x", "max_vel_y", "min_vel_y",
+        "max_vel_theta", "min_vel_theta", "acc_lim_x", "acc_lim_y", "acc_lim_theta",
+        "twist_rotation_compensation")] + [("maintain_vel_components_rate", _i), ("_pad", _i)]
+
+
+class HmpGeneral(C.Structure):
+    _fields_ = [(n, _d) for n in ("sim_time", "sim_granularity", "angular_sim_granularity", "sim_period",
+                                  "people_prediction_dt")] + [("discretize_by_time", _i), ("_pad", _i)]
+
+
+class HmpSfm(C.Structure):
+    _fields_ = [(n, _d) for n in (
+        "fov", "mass", "internal_force_factor", "static_interaction_force_factor",
+        "dynamic_interaction_force_factor", "min_force", "max_force", "speed_desired", "relaxation_time",
+        "an", "bn", "cn", "ap", "bp", "cp", "aw", "bw")] + [
+        ("fov_factor_method", _i), ("filter_forces", _i), ("disable_interaction_forces", _i), ("_pad", _i)]
+
+
+class HmpFis(C.Structure):
+    _fields_ = [("force_factor", _d), ("human_action_range", _d), ("fov", _d), ("fov_factor_method", _i), ("_pad", _i)]
+
+
+class HmpCosts(C.Structure):
+    _fields_ = [
+        ("scale", _d * NUM_COSTS),
+        ("occdist_separation", _d), ("occdist_separation_kernel", _i), ("occdist_sum_scores", _i),
+        ("xshift", _d * NUM_MAPGRIDS), ("yshift", _d * NUM_MAPGRIDS), ("stop_on_failure", _i * NUM_MAPGRIDS),
+        ("neighbour_kernel_size", _i * NUM_MAPGRIDS), ("neighbour_cost_multiplier", _d * NUM_MAPGRIDS),
+        ("unsat_max_trans_vel", _d), ("unsat_max_vel_x", _d), ("unsat_max_vel_y", _d),
+        ("backward_penalty", _d), ("ttc_rollout_time", _d), ("ttc_collision_distance", _d),
+        ("hd_fov_person", _d), ("hd_person_model_radius", _d), ("hd_robot_circumradius", _d), ("hd_max_speed", _d),
+        ("ps_max_speed", _d), ("ps_min_dist", _d),
+        ("unsat_whole_horizon", _i), ("hd_whole_horizon", _i), ("psi_whole_horizon", _i),
+        ("fsi_whole_horizon", _i), ("ps_whole_horizon", _i), ("_pad", _i),
+    ]
+
+
+class HmpParams(C.Structure):
+    _fields_ = [("limits", HmpLimits), ("general", HmpGeneral), ("sfm", HmpSfm), ("fis", HmpFis), ("costs", HmpCosts)]
+
+
+class HmpObstacle(C.Structure):
+    _fields_ = [(n, _d) for n in ("robot_x", "robot_y", "robot_yaw", "obj_x", "obj_y", "obj_yaw", "vx", "vy", "vth")] + [
+        ("force_dynamic", _i), ("_pad", _i)]
+
+
+class HmpPerson(C.Structure):
+    _fields_ = [(n, _d) for n in ("x", "y", "yaw", "vx", "vy", "vth", "cov_xx", "cov_xy", "cov_yx", "cov_yy")]
+
+
+class HmpGroup(C.Structure):
+    _fields_ = [(n, _d) for n in ("x", "y", "yaw", "span_x", "span_y", "cov_xx", "cov_xy", "cov_yy")]
+
+
+class HmpWorld(C.Structure):
+    _fields_ = [(n, _d) for n in (
+        "robot_x", "robot_y", "robot_yaw", "vel_x", "vel_y", "vel_th",
+        "goal_local_x", "goal_local_y", "goal_local_yaw", "goal_x", "goal_y", "goal_yaw")] + [
+        ("obstacles", C.POINTER(HmpObstacle)), ("people", C.POINTER(HmpPerson)), ("groups", C.POINTER(HmpGroup)),
+        ("n_obstacles", _i), ("n_people", _i), ("n_groups", _i), ("_pad", _i)]
+
+
+class HmpSampling(C.Structure):
+    _fields_ = [("amp_min", _d * NUM_AMPLIFIERS), ("amp_max", _d * NUM_AMPLIFIERS),
+                ("amp_granularity", _d * NUM_AMPLIFIERS)]
+
+
+class HmpSample(C.Structure):
+    _fields_ = [("amp", _d * NUM_AMPLIFIERS)]
+
+
+class HmpResult(C.Structure):
+    _fields_ = [
+        ("status", _i), ("best_index", _i), ("n_candidates", _i), ("n_generated", _i), ("n_valid", _i), ("n_poses", _i),
+        ("best_total", _d), ("costs", _d * NUM_COSTS), ("xv", _d), ("yv", _d), ("thetav", _d), ("time_delta", _d),
+        ("amplifiers", _d * NUM_AMPLIFIERS), ("highest_valid_cost", _d * NUM_MAPGRIDS),
+        ("gpu_ms", _d), ("gpu_ms_select", _d),
+    ]
+
+
+# Every symbol include/hmp_planner.h declares (checked by tests/test_capi_symbols.py)
+ABI_SYMBOLS = (
+    "hmp_create", "hmp_destroy", "hmp_last_error", "hmp_abi_version", "hmp_set_params", "hmp_set_costmap",
+    "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
+    "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
+    "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count",
+)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Loads lib/libhmp_planner.so (built by __graft_entry__.build()). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "humap_local_planner_b200 has no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    P = C.POINTER
+    lib.hmp_create.restype = C.c_void_p
+    lib.hmp_create.argtypes = [C.c_int]
+    lib.hmp_destroy.restype = None
+    lib.hmp_destroy.argtypes = [C.c_void_p]
+    lib.hmp_last_error.restype = C.c_char_p
+    lib.hmp_last_error.argtypes = []
+    lib.hmp_abi_version.restype = C.c_int
+    lib.hmp_set_params.argtypes = [C.c_void_p, P(HmpParams)]
+    lib.hmp_set_costmap.argtypes = [C.c_void_p, C.c_void_p, _i, _i, _d, _d, _d]
+    lib.hmp_set_mapgrid.argtypes = [C.c_void_p, _i, C.c_void_p, _d]
+    lib.hmp_set_footprint.argtypes = [C.c_void_p, C.c_void_p, _i]
+    lib.hmp_plan.argtypes = [C.c_void_p, P(HmpWorld), P(HmpSampling), C.c_void_p, _i, P(HmpResult), C.c_void_p, _i]
+    lib.hmp_plan_batch.argtypes = [C.c_void_p, P(HmpWorld), _i, C.c_void_p, C.c_void_p, C.c_void_p, P(HmpSampling),
+                                   P(HmpResult)]
+    lib.hmp_replan_resident.argtypes = [C.c_void_p, P(HmpResult)]
+    lib.hmp_get_explored_totals.argtypes = [C.c_void_p, C.c_void_p, _i]
+    lib.hmp_explain.argtypes = [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hmp_debug_world_to_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hmp_debug_footprint_cost.argtypes = [C.c_void_p, C.c_void_p, _i, C.c_void_p]
+    lib.hmp_debug_fis.argtypes = [C.c_void_p, C.c_void_p, _i, C.c_void_p]
+    lib.hmp_debug_last_forces.argtypes = [C.c_void_p, _i, C.c_void_p]
+    lib.hmp_num_steps.argtypes = [C.c_void_p]
+    lib.hmp_launch_count.restype = C.c_int64
+    lib.hmp_launch_count.argtypes = [C.c_void_p]
+    for name in ("hmp_set_params", "hmp_set_costmap", "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan",
+                 "hmp_plan_batch", "hmp_replan_resident", "hmp_get_explored_totals", "hmp_explain",
+                 "hmp_debug_world_to_map", "hmp_debug_footprint_cost", "hmp_debug_fis", "hmp_debug_last_forces",
+                 "hmp_num_steps"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class HmpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"hmp error {code}: {message}")
+        self.code = code
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """Host-side container of one planning cycle's inputs; keeps the ctypes arrays alive."""
+
+    def __init__(self, world: HmpWorld, obstacles, people, groups, cells: np.ndarray, origin_x: float, origin_y: float,
+                 resolution: float, grids: Sequence[np.ndarray], footprint: np.ndarray,
+                 hv_prev: Sequence[float] = (0.0, 0.0, 0.0, 0.0)):
+        self.world = world
+        self._obstacles, self._people, self._groups = obstacles, people, groups
+        self.cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        self.size_y, self.size_x = self.cells.shape
+        self.origin_x, self.origin_y, self.resolution = float(origin_x), float(origin_y), float(resolution)
+        self.grids = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
+        self.footprint = np.ascontiguousarray(footprint, dtype=np.float64)
+        self.hv_prev = tuple(float(v) for v in hv_prev)
+
+
+class Planner:
+    """One GPU context (hmp_create). Not re-entrant, like the reference (it plans under cfg_->getMutex())."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._ctx = self._lib.hmp_create(int(device))
+        if not self._ctx:
+            raise HmpError(HMP_E_CUDA, self._lib.hmp_last_error().decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.hmp_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise HmpError(rc, self._lib.hmp_last_error().decode())
+
+    # ---- configuration -------------------------------------------------------------------------
+    def set_params(self, params: HmpParams):
+        self._check(self._lib.hmp_set_params(self._ctx, C.byref(params)))
+
+    def set_costmap(self, cells: np.ndarray, origin_x: float, origin_y: float, resolution: float):
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        sy, sx = cells.shape
+        self._check(self._lib.hmp_set_costmap(self._ctx, _ptr(cells), sx, sy, origin_x, origin_y, resolution))
+
+    def set_mapgrid(self, grid: int, target_dist: np.ndarray, hv_prev: float = 0.0):
+        t = np.ascontiguousarray(target_dist, dtype=np.float64)
+        self._check(self._lib.hmp_set_mapgrid(self._ctx, grid, _ptr(t), float(hv_prev)))
+
+    def set_footprint(self, xy: np.ndarray):
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        self._check(self._lib.hmp_set_footprint(self._ctx, _ptr(xy), xy.shape[0]))
+
+    def set_scene(self, scene: Scene):
+        self.set_costmap(scene.cells, scene.origin_x, scene.origin_y, scene.resolution)
+        for g in range(NUM_MAPGRIDS):
+            self.set_mapgrid(g, scene.grids[g], scene.hv_prev[g])
+        self.set_footprint(scene.footprint)
+
+    # ---- hot path ------------------------------------------------------------------------------
+    def plan(self, world: HmpWorld, sampling: HmpSampling, extra: Optional[np.ndarray] = None, want_poses: bool = True):
+        res = HmpResult()
+        n_extra = 0
+        ex = None
+        if extra is not None:
+            ex = np.ascontiguousarray(extra, dtype=np.float64).reshape(-1, NUM_AMPLIFIERS)
+            n_extra = ex.shape[0]
+        poses = np.zeros((MAX_STEPS, 3), dtype=np.float64) if want_poses else None
+        self._check(self._lib.hmp_plan(self._ctx, C.byref(world), C.byref(sampling), _ptr(ex), n_extra, C.byref(res),
+                                       _ptr(poses), MAX_STEPS if want_poses else 0))
+        return res, (poses[: max(res.n_poses, 0)] if want_poses else None)
+
+    def plan_batch(self, worlds: Sequence[HmpWorld], cells: np.ndarray, grids: Sequence[np.ndarray],
+                   sampling: HmpSampling, hv_prev: Optional[np.ndarray] = None):
+        """cells: [n][size_y][size_x] uint8; grids: 4 arrays [n][size_y][size_x] float64."""
+        n = len(worlds)
+        arr = (HmpWorld * n)(*worlds)
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        gs = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
+        gp = (C.c_void_p * NUM_MAPGRIDS)(*[g.ctypes.data for g in gs])
+        hv = None if hv_prev is None else np.ascontiguousarray(hv_prev, dtype=np.float64)
+        res = (HmpResult * n)()
+        self._check(self._lib.hmp_plan_batch(self._ctx, arr, n, _ptr(cells), gp, _ptr(hv), C.byref(sampling), res))
+        return list(res)
+
+    def replan_resident(self, n_scenes: int = 1):
+        res = (HmpResult * n_scenes)()
+        self._check(self._lib.hmp_replan_resident(self._ctx, res))
+        return list(res)
+
+    # ---- diagnostics ---------------------------------------------------------------------------
+    def explored_totals(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.float64)
+        self._check(self._lib.hmp_get_explored_totals(self._ctx, _ptr(out), n))
+        return out
+
+    def num_steps(self) -> int:
+        return int(self._lib.hmp_num_steps(self._ctx))
+
+    def explain(self, indices: Sequence[int], with_forces: bool = False):
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        n = idx.shape[0]
+        T = self.num_steps()
+        costs = np.zeros((n, NUM_COSTS))
+        seeds = np.zeros((n, 3))
+        poses = np.zeros((n, T, 3))
+        nsteps = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.hmp_explain(self._ctx, _ptr(idx), n, _ptr(costs), _ptr(seeds), _ptr(poses), _ptr(nsteps)))
+        out = {"costs": costs, "seeds": seeds, "poses": poses, "n_poses": nsteps}
+        if with_forces:
+            forces = np.zeros((n, T, 8))
+            self._check(self._lib.hmp_debug_last_forces(self._ctx, n, _ptr(forces)))
+            out["forces"] = forces
+        return out
+
+    def debug_world_to_map(self, wx: np.ndarray, wy: np.ndarray):
+        wx = np.ascontiguousarray(wx, dtype=np.float64)
+        wy = np.ascontiguousarray(wy, dtype=np.float64)
+        n = wx.shape[0]
+        mx, my, ok = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        self._check(self._lib.hmp_debug_world_to_map(self._ctx, _ptr(wx), _ptr(wy), n, _ptr(mx), _ptr(my), _ptr(ok)))
+        return mx, my, ok
+
+    def debug_footprint_cost(self, xyt: np.ndarray) -> np.ndarray:
+        xyt = np.ascontiguousarray(xyt, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(xyt.shape[0])
+        self._check(self._lib.hmp_debug_footprint_cost(self._ctx, _ptr(xyt), xyt.shape[0], _ptr(out)))
+        return out
+
+    def debug_fis(self, in4: np.ndarray) -> np.ndarray:
+        in4 = np.ascontiguousarray(in4, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros((in4.shape[0], 2))
+        self._check(self._lib.hmp_debug_fis(self._ctx, _ptr(in4), in4.shape[0], _ptr(out)))
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.hmp_launch_count(self._ctx))

@@ -1,0 +1,1150 @@
+/*
+ * hmp_api.cu -- host side of the C ABI declared in include/hmp_planner.h.
+ *
+ * Flattens HumapConfig-like parameters and the per-cycle World into the device layout of hmp_device.h,
+ * uploads them, launches the rollout+scoring+selection kernel (hmp_kernels.cu) and reads back the
+ * winner. There is NO CPU implementation of the path in this library: if CUDA is unavailable every
+ * entry point fails with HMP_E_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "hmp_device.h"
+
+static_assert(sizeof(DevParams) % 16 == 0, "DevParams is copied with cp.async.bulk (16-byte granules)");
+static_assert(sizeof(DevScene) % 16 == 0, "DevScene header must keep the arrays 16-byte aligned");
+static_assert(sizeof(DevDynamic) == 32 && sizeof(DevPerson) == 64 && sizeof(DevGroup) == 32 && sizeof(DevStatic) == 8,
+              "device record sizes are relied upon by the float4 loads in the kernel");
+
+extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_stride, int costmap_in_smem);
+extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
+extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int* blocks_per_sm);
+extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
+                                                   int* my, int* ok, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
+                                                     double* cost, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_fis(const float* in4, int n, float* out2, cudaStream_t stream);
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+void set_err(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+#define CU(call)                                                                              \
+	do {                                                                                      \
+		cudaError_t e__ = (call);                                                             \
+		if (e__ != cudaSuccess) {                                                             \
+			set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return HMP_E_CUDA;                                                                \
+		}                                                                                     \
+	} while (0)
+
+constexpr double PI = 3.14159265358979323846;
+inline double wrap(double a) { return std::atan2(std::sin(a), std::cos(a)); }
+
+// A device buffer that only grows.
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return HMP_OK;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = std::max<size_t>(bytes, 256);
+		CU(cudaMalloc(&p, want));
+		cap = want;
+		return HMP_OK;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+struct HostBuf {  // pinned
+	void* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return HMP_OK;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = std::max<size_t>(bytes, 256);
+		CU(cudaMallocHost(&p, want));
+		cap = want;
+		return HMP_OK;
+	}
+	void release() {
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+// SocialTrajectoryGenerator::computeAmplifierSamples, social_trajectory_generator.cpp:465-498
+int amplifier_samples(double amp_min, double amp_max, double granularity, double* out, int cap) {
+	int n = 0;
+	double span = (amp_max - amp_min) / granularity;
+	if (!(span == span) || std::fabs(span) > 1e9) return -1;
+	int num = (int)std::ceil(span);
+	for (int i = 0; i <= num; i++) {
+		double v = amp_min + granularity * i;
+		if (n >= cap) return -1;
+		if (v > amp_max) {
+			out[n++] = amp_max;
+			break;
+		}
+		out[n++] = v;
+	}
+	if (n == 0) out[n++] = 0.0;
+	return n;
+}
+
+}  // namespace
+
+struct HmpContext {
+	int device = 0;
+	int sm_count = 0;
+	size_t max_smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
+	int64_t launches = 0;
+
+	HmpParams params{};
+	bool have_params = false;
+	int size_x = 0, size_y = 0;
+	double origin_x = 0, origin_y = 0, resolution = 0;
+	bool have_costmap = false;
+	bool have_grid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
+	double hv_prev[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
+	std::vector<double> footprint;
+	bool have_footprint = false;
+
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
+	HostBuf h_stage, h_out;
+	uint32_t costmap_stride = 0;
+
+	// last plan
+	int last_n_candidates = 0, last_T = 0, last_n_scenes = 0;
+	uint32_t last_scene_stride = 0;
+	DevParams last_dev_params{};
+	std::vector<double> last_amp_table;
+	std::vector<HmpSample> last_extra;
+	bool last_valid = false;
+};
+
+namespace {
+
+// ---- flattening ------------------------------------------------------------------------------------
+int compute_steps(const HmpGeneral& g, double speed_linear, double speed_angular) {
+	// SocialTrajectoryGenerator::computeStepsNumber, social_trajectory_generator.cpp:584-599
+	if (g.discretize_by_time) return (int)std::ceil(g.sim_time / g.sim_granularity);
+	double sd = speed_linear * g.sim_time;
+	double sa = std::fabs(speed_angular) * g.sim_time;
+	return (int)std::ceil(std::max(sd / g.sim_granularity, sa / g.angular_sim_granularity));
+}
+
+int build_dev_params(const HmpContext* ctx, const HmpSampling* sampling, int n_extra, int T, DevParams& D,
+                     std::vector<double>& amp_table) {
+	const HmpParams& P = ctx->params;
+	std::memset(&D, 0, sizeof(D));
+	D.T = T;
+	D.dt_d = P.general.sim_time / T;
+	D.dt = (float)D.dt_d;
+	D.people_dt = (float)P.general.people_prediction_dt;
+	D.ttc_rollout_time_d = P.costs.ttc_rollout_time;
+	{
+		int n = 0;  // iterations of `for (double t = 0.0; t < ttc_rollout_time_; t += dt)`, ttc_cost_function.cpp:100
+		for (double t = 0.0; t < P.costs.ttc_rollout_time; t += D.dt_d) {
+			if (++n > 100000) break;
+		}
+		D.n_ttc_extra = n;
+	}
+	const HmpLimits& L = P.limits;
+	D.max_vel_x = (float)L.max_vel_x;
+	D.min_vel_x = (float)L.min_vel_x;
+	D.max_vel_y = (float)L.max_vel_y;
+	D.min_vel_y = (float)L.min_vel_y;
+	D.max_vel_theta = (float)L.max_vel_theta;
+	D.min_vel_theta = (float)L.min_vel_theta;
+	D.max_vel_trans = (float)L.max_vel_trans;
+	D.min_vel_trans = (float)L.min_vel_trans;
+	D.acc_x = (float)L.acc_lim_x;
+	D.acc_y = (float)L.acc_lim_y;
+	D.acc_th = (float)L.acc_lim_theta;
+	D.acc_decel = (float)std::hypot(L.acc_lim_x, L.acc_lim_y);
+	D.rot_comp = (float)L.twist_rotation_compensation;
+	D.back_max = (float)((L.min_vel_x < 0.0) ? std::fabs(L.min_vel_x) : 0.0);
+	D.maintain_rate = L.maintain_vel_components_rate != 0;
+
+	const HmpSfm& S = P.sfm;
+	D.fov_method = S.fov_factor_method;
+	D.filter_forces = S.filter_forces != 0;
+	D.disable_interaction = S.disable_interaction_forces != 0;
+	D.mass = (float)S.mass;
+	D.m_over_tau = (float)(S.mass * (1 / (double)(float)S.relaxation_time));
+	D.k_int = (float)S.internal_force_factor;
+	D.k_stat = (float)S.static_interaction_force_factor;
+	D.k_dyn = (float)S.dynamic_interaction_force_factor;
+	D.min_force = (float)S.min_force;
+	D.max_force = (float)S.max_force;
+	// computeFactorFOV(angle, 2 * cfg.fov, gaussian): half angle cfg.fov, variance cfg.fov^2, PDF not normalised to 1
+	D.fov_half = (float)S.fov;
+	D.fov_gauss_scale = (float)(1.0 / (std::sqrt(S.fov * S.fov) * std::sqrt(2.0 * PI)));
+	D.fov_neg_inv_2var = (float)(-1.0 / (2.0 * S.fov * S.fov));
+	const double base[9] = {S.speed_desired, S.an, S.bn, S.cn, S.ap, S.bp, S.cp, S.aw, S.bw};
+	for (int i = 0; i < 9; ++i) D.base[i] = (float)base[i];
+
+	const HmpFis& F = P.fis;
+	D.fis_on = (!D.disable_interaction && !(F.force_factor <= 0.0)) ? 1 : 0;
+	D.fis_fov_method = F.fov_factor_method;
+	D.fis_force_factor = (float)F.force_factor;
+	D.fis_range = (float)F.human_action_range;
+	D.fis_fov_half = (float)(F.fov / 2.0);
+	{
+		double var = (F.fov / 2.0) * (F.fov / 2.0);
+		D.fis_gauss_scale = (float)(1.0 / (std::sqrt(var) * std::sqrt(2.0 * PI)));
+		D.fis_neg_inv_2var = (float)(-1.0 / (2.0 * var));
+	}
+
+	// amplifier lists
+	amp_table.assign((size_t)HMP_NUM_AMPLIFIERS * HMP_MAX_AMP_VALUES, 0.0);
+	long long total = 1;
+	for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) {
+		int n = amplifier_samples(sampling->amp_min[a], sampling->amp_max[a], sampling->amp_granularity[a],
+		                          &amp_table[(size_t)a * HMP_MAX_AMP_VALUES], HMP_MAX_AMP_VALUES);
+		if (n <= 0) {
+			set_err("amplifier axis %d yields more than %d values or is malformed", a, HMP_MAX_AMP_VALUES);
+			return HMP_E_CAPACITY;
+		}
+		D.amp_n[a] = n;
+		total *= n;
+		if (total > (1ll << 30)) {
+			set_err("sampling grid has more than 2^30 candidates");
+			return HMP_E_CAPACITY;
+		}
+	}
+	D.n_grid = (int)total;
+	D.n_candidates = (int)total + n_extra;
+
+	D.size_x = ctx->size_x;
+	D.size_y = ctx->size_y;
+	D.origin_x = ctx->origin_x;
+	D.origin_y = ctx->origin_y;
+	D.resolution = ctx->resolution;
+	D.inv_resolution = 1.0 / ctx->resolution;
+
+	const HmpCosts& C = P.costs;
+	for (int k = 0; k < HMP_NUM_COSTS; ++k) D.scale[k] = C.scale[k];
+	D.n_footprint = (int)ctx->footprint.size() / 2;
+	for (int i = 0; i < D.n_footprint; ++i) {
+		D.footprint_x[i] = ctx->footprint[2 * i];
+		D.footprint_y[i] = ctx->footprint[2 * i + 1];
+	}
+	// separation kernel, obstacle_separation_cost_function.cpp:183-219
+	D.n_kernel_pts = 1;
+	D.kernel_dx[0] = D.kernel_dy[0] = 0.0;
+	if (!(std::fabs(C.occdist_separation) < 1e-03)) {
+		static const double cross[4] = {0.0, M_PI_2, M_PI, -M_PI_2};
+		static const double rect[8] = {0.0, M_PI_4, M_PI_2, 3.0 * M_PI_4, M_PI, -3.0 * M_PI_4, -M_PI_2, -M_PI_4};
+		const double* ang = nullptr;
+		int n = 0;
+		if (C.occdist_separation_kernel == 0) {
+			ang = cross;
+			n = 4;
+		} else if (C.occdist_separation_kernel == 1) {
+			ang = rect;
+			n = 8;
+		}
+		for (int i = 0; i < n; ++i) {
+			D.kernel_dx[1 + i] = C.occdist_separation * std::cos(ang[i]);
+			D.kernel_dy[1 + i] = C.occdist_separation * std::sin(ang[i]);
+		}
+		D.n_kernel_pts = 1 + n;
+	}
+	D.occdist_sum = C.occdist_sum_scores != 0;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		D.mg_stop_on_failure[g] = C.stop_on_failure[g] != 0;
+		D.mg_kernel[g] = C.neighbour_kernel_size[g];
+		D.mg_xshift[g] = C.xshift[g];
+		D.mg_yshift[g] = C.yshift[g];
+	}
+	D.unsat_max_trans = (float)C.unsat_max_trans_vel;
+	D.unsat_max_x = (float)C.unsat_max_vel_x;
+	D.unsat_max_y = (float)C.unsat_max_vel_y;
+	D.backward_penalty = (float)C.backward_penalty;
+	D.ttc_collision_distance = (float)C.ttc_collision_distance;
+	{
+		double var = (C.hd_fov_person / 2.0) * (C.hd_fov_person / 2.0);
+		D.hd_neg_inv_2var_fov = (float)(-1.0 / (2.0 * var));
+	}
+	D.hd_dmin = (float)(C.hd_robot_circumradius + C.hd_person_model_radius);
+	D.hd_inv_max_speed = (float)(1.0 / C.hd_max_speed);
+	D.ps_min_dist = (float)C.ps_min_dist;
+	D.ps_inv_max_speed = (float)(1.0 / C.ps_max_speed);
+	D.unsat_whole = C.unsat_whole_horizon != 0;
+	D.hd_whole = C.hd_whole_horizon != 0;
+	D.psi_whole = C.psi_whole_horizon != 0;
+	D.fsi_whole = C.fsi_whole_horizon != 0;
+	D.ps_whole = C.ps_whole_horizon != 0;
+	return HMP_OK;
+}
+
+size_t scene_blob_bytes(const HmpWorld& w) {
+	// worst case: every obstacle appears in both the dynamic and the static array (App. A #5)
+	size_t b = sizeof(DevScene);
+	b += ((size_t)w.n_obstacles * sizeof(DevStatic) + 15) / 16 * 16;
+	b += (size_t)w.n_obstacles * sizeof(DevDynamic);
+	b += (size_t)w.n_people * sizeof(DevPerson);
+	b += (size_t)w.n_groups * sizeof(DevGroup);
+	return (b + 15) / 16 * 16;
+}
+
+// Packs one World (+ people / groups) into `out` (scene_blob_bytes(w) bytes, zero-filled by the caller).
+void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev, double dt, unsigned char* out) {
+	const HmpParams& P = ctx->params;
+	DevScene H;
+	std::memset(&H, 0, sizeof(H));
+	H.x0 = w.robot_x;
+	H.y0 = w.robot_y;
+	H.yaw0 = wrap(w.robot_yaw);
+	// computeVelocityGlobal(vel_, pose_), humap_planner.cpp:366-369
+	double cy = std::cos(H.yaw0), sy = std::sin(H.yaw0);
+	H.u0x = (float)(w.vel_x * cy - w.vel_y * sy);
+	H.u0y = (float)(w.vel_x * sy + w.vel_y * cy);
+	H.u0w = (float)w.vel_th;
+	H.vlx = (float)w.vel_x;
+	H.vly = (float)w.vel_y;
+	H.vlw = (float)w.vel_th;
+	H.glx = (float)(w.goal_local_x - w.robot_x);
+	H.gly = (float)(w.goal_local_y - w.robot_y);
+	H.gx = (float)(w.goal_x - w.robot_x);
+	H.gy = (float)(w.goal_y - w.robot_y);
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) H.hv_prev[g] = hv_prev ? hv_prev[g] : 0.0;
+
+	std::vector<DevStatic> st_always, st_later;
+	std::vector<DevDynamic> dy_always, dy_first;
+	for (int i = 0; i < w.n_obstacles; ++i) {
+		const HmpObstacle& o = w.obstacles[i];
+		double len3 = std::sqrt(o.vx * o.vx + o.vy * o.vy + o.vth * o.vth);  // Vector::calculateLength is 3-D (App. A #4)
+		bool moving = len3 > 0.035;                                          // world.h:110
+		bool dyn0 = (o.force_dynamic != 0) || moving;                        // world.cpp:49
+		double d0x = o.obj_x - o.robot_x, d0y = o.obj_y - o.robot_y;
+		if (!dyn0) {
+			st_always.push_back({(float)d0x, (float)d0y});
+			continue;
+		}
+		DevDynamic d;
+		d.d0x = (float)d0x;
+		d.d0y = (float)d0y;
+		d.vx = (float)o.vx;
+		d.vy = (float)o.vy;
+		d.psi0 = (float)wrap(o.robot_yaw);
+		d.dir_beta = (float)wrap(std::atan2(o.vy, o.vx));
+		d.speed = (float)std::hypot(o.vx, o.vy);
+		d._pad = 0.f;
+		if (moving) {
+			dy_always.push_back(d);
+		} else {
+			// dynamic at step 0 only: advanced once by v dt in the first World::predict, then static (world.cpp:101-110)
+			dy_first.push_back(d);
+			st_later.push_back({(float)(d0x + o.vx * dt), (float)(d0y + o.vy * dt)});
+		}
+	}
+	H.n_static0 = (int)st_always.size();
+	H.n_static = (int)(st_always.size() + st_later.size());
+	H.n_dynamic_later = (int)dy_always.size();
+	H.n_dynamic = (int)(dy_always.size() + dy_first.size());
+	H.n_people = w.n_people;
+	H.n_groups = w.n_groups;
+	uint32_t off = sizeof(DevScene);
+	H.off_static = off;
+	off += (uint32_t)(((size_t)H.n_static * sizeof(DevStatic) + 15) / 16 * 16);
+	H.off_dynamic = off;
+	off += (uint32_t)((size_t)H.n_dynamic * sizeof(DevDynamic));
+	H.off_people = off;
+	off += (uint32_t)((size_t)H.n_people * sizeof(DevPerson));
+	H.off_groups = off;
+	off += (uint32_t)((size_t)H.n_groups * sizeof(DevGroup));
+	H.blob_bytes = (off + 15) / 16 * 16;
+
+	std::memcpy(out, &H, sizeof(H));
+	DevStatic* ps = reinterpret_cast<DevStatic*>(out + H.off_static);
+	for (size_t i = 0; i < st_always.size(); ++i) ps[i] = st_always[i];
+	for (size_t i = 0; i < st_later.size(); ++i) ps[st_always.size() + i] = st_later[i];
+	DevDynamic* pd = reinterpret_cast<DevDynamic*>(out + H.off_dynamic);
+	for (size_t i = 0; i < dy_always.size(); ++i) pd[i] = dy_always[i];
+	for (size_t i = 0; i < dy_first.size(); ++i) pd[dy_always.size() + i] = dy_first[i];
+
+	DevPerson* pp = reinterpret_cast<DevPerson*>(out + H.off_people);
+	for (int i = 0; i < w.n_people; ++i) {
+		const HmpPerson& p = w.people[i];
+		DevPerson d;
+		d.x = (float)(p.x - w.robot_x);
+		d.y = (float)(p.y - w.robot_y);
+		double yaw = wrap(p.yaw);
+		d.yaw = (float)yaw;
+		d.vth = (float)p.vth;
+		d.vx = (float)p.vx;
+		d.vy = (float)p.vy;
+		d.cos0 = (float)std::cos(yaw);
+		d.sin0 = (float)std::sin(yaw);
+		d.cxx = (float)p.cov_xx;
+		d.cxy = (float)p.cov_xy;
+		d.cyx = (float)p.cov_yx;
+		d.cyy = (float)p.cov_yy;
+		// personal_space_intrusion_cost_function.cpp:55-58
+		double vel_lin = std::hypot(p.vx, p.vy);
+		double var_front = std::max(2.0 * vel_lin, 0.5);
+		d.var_front = (float)var_front;
+		d.var_side = (float)((2.0 / 3.0) * var_front);
+		d.var_rear = (float)((1.0 / 2.0) * var_front);
+		d.radius_eff = (float)(P.costs.hd_person_model_radius + std::sqrt(0.5 * (p.cov_xx + p.cov_yy)));
+		pp[i] = d;
+	}
+	DevGroup* pg = reinterpret_cast<DevGroup*>(out + H.off_groups);
+	for (int i = 0; i < w.n_groups; ++i) {
+		const HmpGroup& g = w.groups[i];
+		// fformation_space_intrusion_cost_function.cpp:60-61: variance = (span / 2 / 2)^2 along the group's axes
+		double var_x = std::pow((g.span_x / 2.0) / 2.0, 2), var_y = std::pow((g.span_y / 2.0) / 2.0, 2);
+		double yaw = wrap(g.yaw);
+		double c = std::cos(yaw), s = std::sin(yaw);
+		double a = var_x * c * c + var_y * s * s + g.cov_xx;
+		double b = (var_x - var_y) * c * s + g.cov_xy;
+		double cc = var_x * s * s + var_y * c * c + g.cov_yy;
+		double det = a * cc - b * b;
+		DevGroup d;
+		std::memset(&d, 0, sizeof(d));
+		d.x = (float)(g.x - w.robot_x);
+		d.y = (float)(g.y - w.robot_y);
+		d.ia = (float)(cc / det);
+		d.ib = (float)(-b / det);
+		d.ic = (float)(a / det);
+		pg[i] = d;
+	}
+}
+
+struct CtrlLayout {  // d_ctrl: counters [n][4] u32 | hv_out [n][4] u32 | best_out [n][2] f64
+	size_t off_counters, off_hv, off_best, total;
+};
+CtrlLayout ctrl_layout(int n_scenes) {
+	CtrlLayout c;
+	c.off_counters = 0;
+	c.off_hv = (size_t)n_scenes * 4 * sizeof(unsigned int);
+	c.off_best = c.off_hv + (size_t)n_scenes * 4 * sizeof(unsigned int);
+	c.off_best = (c.off_best + 15) / 16 * 16;
+	c.total = c.off_best + (size_t)n_scenes * 2 * sizeof(double);
+	return c;
+}
+
+int check_ready(const HmpContext* ctx) {
+	if (!ctx) {
+		set_err("null context");
+		return HMP_E_INVALID;
+	}
+	if (!ctx->have_params) {
+		set_err("hmp_set_params has not been called");
+		return HMP_E_NOT_READY;
+	}
+	if (!ctx->have_costmap) {
+		set_err("hmp_set_costmap has not been called");
+		return HMP_E_NOT_READY;
+	}
+	return HMP_OK;
+}
+
+// Common part of hmp_plan / hmp_plan_batch: scenes, costmaps and mapgrids are already on the device.
+struct PlanLaunch {
+	int n_scenes;
+	uint32_t scene_stride;
+	int n_extra;
+	int T;
+};
+
+int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* blocks_x_out, size_t* smem_out,
+                int* costmap_in_smem_out) {
+	const int C = D.n_candidates;
+	size_t cm_bytes = (size_t)ctx->costmap_stride;
+	int in_smem = 1;
+	size_t smem = hmp_dev_smem_bytes(pl.scene_stride, (uint32_t)cm_bytes, 1);
+	if (smem > ctx->max_smem_optin || cm_bytes > (1u << 19)) {
+		in_smem = 0;
+		smem = hmp_dev_smem_bytes(pl.scene_stride, (uint32_t)cm_bytes, 0);
+		if (smem > ctx->max_smem_optin) {
+			set_err("scene does not fit shared memory (%zu bytes needed, %zu available)", smem, ctx->max_smem_optin);
+			return HMP_E_CAPACITY;
+		}
+	}
+	int bps = 0;
+	CU(hmp_dev_occupancy(smem, &bps));
+	if (bps < 1) {
+		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
+		return HMP_E_CUDA;
+	}
+	// persistent blocks: fill the GPU once; with many scenes give each scene fewer blocks
+	long long resident = (long long)ctx->sm_count * bps;
+	long long need = ((long long)C + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK;
+	long long per_scene = std::max<long long>(1, std::min<long long>(need, (resident + pl.n_scenes - 1) / pl.n_scenes));
+	*blocks_x_out = (int)per_scene;
+	*smem_out = smem;
+	*costmap_in_smem_out = in_smem;
+	return HMP_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+const char* hmp_last_error(void) { return g_err; }
+int hmp_abi_version(void) { return HMP_ABI_VERSION; }
+
+HmpContext* hmp_create(int device_id) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		set_err("no usable CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+		return nullptr;
+	}
+	if (device_id < 0 || device_id >= n) {
+		set_err("device %d out of range (%d devices)", device_id, n);
+		return nullptr;
+	}
+	if ((e = cudaSetDevice(device_id)) != cudaSuccess) {
+		set_err("cudaSetDevice(%d): %s", device_id, cudaGetErrorString(e));
+		return nullptr;
+	}
+	cudaDeviceProp prop;
+	if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+		set_err("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+		return nullptr;
+	}
+	if (prop.major != 10) {
+		set_err("device %d is sm_%d%d; this library carries sm_100a code only", device_id, prop.major, prop.minor);
+		return nullptr;
+	}
+	HmpContext* ctx = new (std::nothrow) HmpContext();
+	if (!ctx) {
+		set_err("out of memory");
+		return nullptr;
+	}
+	ctx->device = device_id;
+	ctx->sm_count = prop.multiProcessorCount;
+	ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+	    cudaEventCreate(&ctx->evm) != cudaSuccess ||
+	    hmp_dev_configure(ctx->max_smem_optin) != cudaSuccess) {
+		set_err("context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return nullptr;
+	}
+	return ctx;
+}
+
+void hmp_destroy(HmpContext* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg};
+	for (DevBuf* b : bufs) b->release();
+	ctx->h_stage.release();
+	ctx->h_out.release();
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->evm) cudaEventDestroy(ctx->evm);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int hmp_set_params(HmpContext* ctx, const HmpParams* params) {
+	if (!ctx || !params) {
+		set_err("null argument");
+		return HMP_E_INVALID;
+	}
+	if (!(params->general.sim_time > 0.0) || !(params->general.sim_granularity > 0.0)) {
+		set_err("sim_time and sim_granularity must be positive");
+		return HMP_E_INVALID;
+	}
+	ctx->params = *params;
+	ctx->have_params = true;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y, double origin_x, double origin_y,
+                    double resolution) {
+	if (!ctx || !cells || size_x <= 0 || size_y <= 0 || !(resolution > 0.0)) {
+		set_err("bad costmap arguments");
+		return HMP_E_INVALID;
+	}
+	if ((long long)size_x * size_y >= (1ll << 24)) {
+		set_err("costmap has 2^24 cells or more: MapGrid distances would not be exact in FP32");
+		return HMP_E_CAPACITY;
+	}
+	CU(cudaSetDevice(ctx->device));
+	if (size_x != ctx->size_x || size_y != ctx->size_y) {
+		for (bool& b : ctx->have_grid) b = false;
+	}
+	size_t cells_n = (size_t)size_x * size_y;
+	uint32_t stride = (uint32_t)((cells_n + 127) / 128 * 128);
+	int rc = ctx->d_costmaps.ensure(stride);
+	if (rc) return rc;
+	rc = ctx->d_mapgrids.ensure(cells_n * HMP_NUM_MAPGRIDS * sizeof(float));
+	if (rc) return rc;
+	rc = ctx->h_stage.ensure(std::max<size_t>(stride, cells_n * sizeof(float)));
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	std::memcpy(ctx->h_stage.p, cells, cells_n);
+	std::memset((unsigned char*)ctx->h_stage.p + cells_n, 0, stride - cells_n);
+	CU(cudaMemcpyAsync(ctx->d_costmaps.p, ctx->h_stage.p, stride, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->costmap_stride = stride;
+	ctx->size_x = size_x;
+	ctx->size_y = size_y;
+	ctx->origin_x = origin_x;
+	ctx->origin_y = origin_y;
+	ctx->resolution = resolution;
+	ctx->have_costmap = true;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, double highest_valid_cost_prev) {
+	if (!ctx || !target_dist || grid < 0 || grid >= HMP_NUM_MAPGRIDS) {
+		set_err("bad mapgrid arguments");
+		return HMP_E_INVALID;
+	}
+	if (!ctx->have_costmap) {
+		set_err("hmp_set_costmap must precede hmp_set_mapgrid");
+		return HMP_E_NOT_READY;
+	}
+	CU(cudaSetDevice(ctx->device));
+	size_t n = (size_t)ctx->size_x * ctx->size_y;
+	int rc = ctx->h_stage.ensure(n * sizeof(float));
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	float* f = (float*)ctx->h_stage.p;
+	const double limit = (double)n + 1.0;
+	for (size_t i = 0; i < n; ++i) {
+		double v = target_dist[i];
+		if (!(v >= 0.0) || v > limit || v != std::floor(v)) {
+			set_err("target_dist[%zu] = %g is not a cell count in [0, size_x*size_y+1]", i, v);
+			return HMP_E_INVALID;
+		}
+		f[i] = (float)v;
+	}
+	CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + (size_t)grid * n, f, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->have_grid[grid] = true;
+	ctx->hv_prev[grid] = highest_valid_cost_prev;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_set_footprint(HmpContext* ctx, const double* xy, int32_t n_points) {
+	if (!ctx || n_points < 0 || (n_points > 0 && !xy)) {
+		set_err("bad footprint arguments");
+		return HMP_E_INVALID;
+	}
+	if (n_points > HMP_MAX_FOOTPRINT) {
+		set_err("footprint has %d vertices, limit %d", n_points, HMP_MAX_FOOTPRINT);
+		return HMP_E_CAPACITY;
+	}
+	ctx->footprint.assign(xy, xy + 2 * (size_t)n_points);
+	ctx->have_footprint = true;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+static int validate_world(const HmpWorld* w) {
+	if (!w || w->n_obstacles < 0 || w->n_people < 0 || w->n_groups < 0 || (w->n_obstacles > 0 && !w->obstacles) ||
+	    (w->n_people > 0 && !w->people) || (w->n_groups > 0 && !w->groups)) {
+		set_err("bad world arguments");
+		return HMP_E_INVALID;
+	}
+	return HMP_OK;
+}
+
+// Runs the selection kernel + the winner's detail pass for scenes already resident on the device.
+static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<double>& amp_table, const HmpSample* extra,
+                     int n_extra, const PlanLaunch& pl, HmpResult* results, double* poses_out, int32_t poses_capacity) {
+	const int C = D.n_candidates;
+	const int T = D.T;
+	const int NS = pl.n_scenes;
+	int rc;
+	if ((rc = ctx->d_params.ensure(sizeof(DevParams)))) return rc;
+	if ((rc = ctx->d_amp.ensure(amp_table.size() * sizeof(double)))) return rc;
+	if ((rc = ctx->d_extra.ensure(std::max<size_t>(1, (size_t)n_extra) * sizeof(HmpSample)))) return rc;
+	if ((rc = ctx->d_totals.ensure((size_t)NS * C * sizeof(double)))) return rc;
+	const CtrlLayout cl = ctrl_layout(NS);
+	if ((rc = ctx->d_ctrl.ensure(cl.total))) return rc;
+	// detail buffer per scene: costs[14] seeds[3] poses[T][3] totals[1] (f64) + nposes (i32, padded to 8)
+	const size_t det_doubles = (size_t)HMP_NUM_COSTS + 3 + (size_t)T * 3 + 1;
+	const size_t det_bytes = (det_doubles * sizeof(double) + 8) * NS;
+	if ((rc = ctx->d_detail.ensure(det_bytes))) return rc;
+	if ((rc = ctx->h_out.ensure(det_bytes + cl.total))) return rc;
+
+	int blocks_x = 0, in_smem = 0;
+	size_t smem = 0;
+	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem))) return rc;
+	if ((rc = ctx->d_block_best.ensure((size_t)NS * blocks_x * 2 * sizeof(unsigned long long)))) return rc;
+
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(ctx->d_params.p, &D, sizeof(DevParams), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_amp.p, amp_table.data(), amp_table.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+	if (n_extra > 0) CU(cudaMemcpyAsync(ctx->d_extra.p, extra, (size_t)n_extra * sizeof(HmpSample), cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, cl.total, st));
+
+	unsigned char* ctrl = (unsigned char*)ctx->d_ctrl.p;
+	KernelArgs A;
+	std::memset(&A, 0, sizeof(A));
+	A.params = (const DevParams*)ctx->d_params.p;
+	A.amp_values = (const double*)ctx->d_amp.p;
+	A.extra_samples = (const double*)ctx->d_extra.p;
+	A.scenes = (const uint8_t*)ctx->d_scenes.p;
+	A.scene_stride = pl.scene_stride;
+	A.n_scenes = NS;
+	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
+	A.costmap_stride = ctx->costmap_stride;
+	A.costmap_in_smem = in_smem;
+	A.mapgrids = (const float*)ctx->d_mapgrids.p;
+	A.n_work = C;
+	A.totals = (double*)ctx->d_totals.p;
+	A.block_best = (unsigned long long*)ctx->d_block_best.p;
+	A.counters = (unsigned int*)(ctrl + cl.off_counters);
+	A.hv_out = (unsigned int*)(ctrl + cl.off_hv);
+	A.best_out = (double*)(ctrl + cl.off_best);
+
+	CU(cudaEventRecord(ctx->ev0, st));
+	CU(hmp_dev_launch_plan(&A, blocks_x, 0, smem, st));
+	ctx->launches++;
+	CU(cudaEventRecord(ctx->evm, st));
+	// snapshot the counters (n_generated, n_valid) before the detail pass reuses the work ticket
+	CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes, ctrl, cl.total, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
+
+	// winner's detail pass: one warp per scene re-runs the best candidate with write-back
+	KernelArgs B = A;
+	double* det = (double*)ctx->d_detail.p;
+	B.n_work = 1;
+	B.use_best_index = 1;
+	B.d_costs = det;
+	B.d_seeds = det + (size_t)NS * HMP_NUM_COSTS;
+	B.d_poses = B.d_seeds + (size_t)NS * 3;
+	B.totals = B.d_poses + (size_t)NS * T * 3;
+	B.d_nposes = (int32_t*)(B.totals + NS);
+	B.d_forces = nullptr;
+	CU(hmp_dev_launch_plan(&B, 1, 1, smem, st));
+	ctx->launches++;
+	CU(cudaEventRecord(ctx->ev1, st));
+	CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	float ms = 0.f;
+	CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	float ms_main = 0.f;
+	CU(cudaEventElapsedTime(&ms_main, ctx->ev0, ctx->evm));
+
+	const double* h_det = (const double*)ctx->h_out.p;
+	const double* h_costs = h_det;
+	const double* h_seeds = h_det + (size_t)NS * HMP_NUM_COSTS;
+	const double* h_poses = h_seeds + (size_t)NS * 3;
+	const int32_t* h_nposes = (const int32_t*)(h_poses + (size_t)NS * T * 3 + NS);
+	const unsigned char* h_ctrl = (const unsigned char*)ctx->h_out.p + det_bytes;
+	const unsigned int* h_counters = (const unsigned int*)(h_ctrl + cl.off_counters);
+	const unsigned int* h_hv = (const unsigned int*)(h_ctrl + cl.off_hv);
+	const double* h_best = (const double*)(h_ctrl + cl.off_best);
+	for (int s = 0; s < NS; ++s) {
+		HmpResult& r = results[s];
+		std::memset(&r, 0, sizeof(r));
+		int best = (int)h_best[2 * s + 1];
+		r.best_index = best;
+		r.status = best >= 0 ? 0 : 1;
+		r.n_candidates = C;
+		r.n_generated = (int)h_counters[4 * s + 2];
+		r.n_valid = (int)h_counters[4 * s + 3];
+		r.best_total = best >= 0 ? h_best[2 * s] : -7.0;  // caller pre-sets cost_ = -7, humap_planner.cpp:1364
+		r.time_delta = D.dt_d;
+		r.gpu_ms = ms;
+		r.gpu_ms_select = ms_main;
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+			float f;
+			std::memcpy(&f, &h_hv[4 * s + g], sizeof(f));
+			r.highest_valid_cost[g] = f;
+		}
+		for (int k = 0; k < HMP_NUM_COSTS; ++k) r.costs[k] = std::numeric_limits<double>::quiet_NaN();
+		if (best >= 0) {
+			for (int k = 0; k < HMP_NUM_COSTS; ++k) r.costs[k] = h_costs[(size_t)s * HMP_NUM_COSTS + k];
+			r.xv = h_seeds[3 * s];
+			r.yv = h_seeds[3 * s + 1];
+			r.thetav = h_seeds[3 * s + 2];
+			r.n_poses = h_nposes[s];
+			if (best < D.n_grid) {
+				int rem = best;
+				for (int a = HMP_NUM_AMPLIFIERS - 1; a >= 0; --a) {
+					int n = D.amp_n[a];
+					r.amplifiers[a] = amp_table[(size_t)a * HMP_MAX_AMP_VALUES + rem % n];
+					rem /= n;
+				}
+			} else if (extra) {
+				for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) r.amplifiers[a] = extra[best - D.n_grid].amp[a];
+			}
+			if (poses_out && s == 0) {
+				int n = std::min<int>(r.n_poses, poses_capacity);
+				std::memcpy(poses_out, h_poses + (size_t)s * T * 3, (size_t)n * 3 * sizeof(double));
+			}
+		}
+	}
+	ctx->last_n_candidates = C;
+	ctx->last_T = T;
+	ctx->last_n_scenes = NS;
+	ctx->last_scene_stride = pl.scene_stride;
+	ctx->last_dev_params = D;
+	if (&amp_table != &ctx->last_amp_table) ctx->last_amp_table = amp_table;
+	if (extra != ctx->last_extra.data()) ctx->last_extra.assign(extra, extra + n_extra);
+	ctx->last_valid = true;
+	return HMP_OK;
+}
+
+int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling, const HmpSample* extra, int32_t n_extra,
+             HmpResult* result, double* poses_out, int32_t poses_capacity) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!sampling || !result || n_extra < 0 || (n_extra > 0 && !extra) || (poses_out && poses_capacity < 0)) {
+		set_err("bad plan arguments");
+		return HMP_E_INVALID;
+	}
+	if ((rc = validate_world(world))) return rc;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!ctx->have_grid[g] && ctx->params.costs.scale[HMP_COST_PATH + g] != 0.0) {
+			set_err("hmp_set_mapgrid(%d) has not been called for the current costmap", g);
+			return HMP_E_NOT_READY;
+		}
+	}
+	if (!ctx->have_footprint && ctx->params.costs.scale[HMP_COST_OBSTACLE] != 0.0) {
+		set_err("hmp_set_footprint has not been called");
+		return HMP_E_NOT_READY;
+	}
+	CU(cudaSetDevice(ctx->device));
+	int T = compute_steps(ctx->params.general, std::hypot(world->vel_x, world->vel_y), world->vel_th);
+	if (T < 1 || T > HMP_MAX_STEPS) {
+		set_err("rollout has %d steps, supported 1..%d", T, HMP_MAX_STEPS);
+		return HMP_E_CAPACITY;
+	}
+	DevParams D;
+	std::vector<double> amp_table;
+	if ((rc = build_dev_params(ctx, sampling, n_extra, T, D, amp_table))) return rc;
+
+	size_t blob = scene_blob_bytes(*world);
+	if ((rc = ctx->d_scenes.ensure(blob))) return rc;
+	if ((rc = ctx->h_stage.ensure(blob))) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	std::memset(ctx->h_stage.p, 0, blob);
+	pack_scene(ctx, *world, ctx->hv_prev, D.dt_d, (unsigned char*)ctx->h_stage.p);
+	uint32_t used = reinterpret_cast<DevScene*>(ctx->h_stage.p)->blob_bytes;
+	CU(cudaMemcpyAsync(ctx->d_scenes.p, ctx->h_stage.p, used, cudaMemcpyHostToDevice, ctx->stream));
+	PlanLaunch pl{1, used, n_extra, T};
+	return run_cycle(ctx, D, amp_table, extra, n_extra, pl, result, poses_out, poses_capacity);
+}
+
+int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, const uint8_t* cells,
+                   const double* const target_dist[HMP_NUM_MAPGRIDS], const double* highest_valid_cost_prev,
+                   const HmpSampling* sampling, HmpResult* results) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!worlds || n_scenes <= 0 || !sampling || !results) {
+		set_err("bad batch arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)ctx->size_x * ctx->size_y;
+	int T = -1;
+	size_t stride = 0;
+	for (int s = 0; s < n_scenes; ++s) {
+		if ((rc = validate_world(&worlds[s]))) return rc;
+		int Ts = compute_steps(ctx->params.general, std::hypot(worlds[s].vel_x, worlds[s].vel_y), worlds[s].vel_th);
+		if (T < 0) T = Ts;
+		if (Ts != T) {
+			set_err("scenes of one batch must share the step count (scene %d: %d vs %d)", s, Ts, T);
+			return HMP_E_INVALID;
+		}
+		stride = std::max(stride, scene_blob_bytes(worlds[s]));
+	}
+	if (T < 1 || T > HMP_MAX_STEPS) {
+		set_err("rollout has %d steps, supported 1..%d", T, HMP_MAX_STEPS);
+		return HMP_E_CAPACITY;
+	}
+	DevParams D;
+	std::vector<double> amp_table;
+	if ((rc = build_dev_params(ctx, sampling, 0, T, D, amp_table))) return rc;
+	if ((rc = ctx->d_scenes.ensure(stride * n_scenes))) return rc;
+	// new per-scene costmaps / mapgrids replace the single-scene ones
+	if (cells) {
+		if ((rc = ctx->d_costmaps.ensure((size_t)ctx->costmap_stride * n_scenes))) return rc;
+	}
+	bool any_grid = target_dist && (target_dist[0] || target_dist[1] || target_dist[2] || target_dist[3]);
+	if (any_grid) {
+		if ((rc = ctx->d_mapgrids.ensure(n * HMP_NUM_MAPGRIDS * sizeof(float) * n_scenes))) return rc;
+	}
+	size_t stage = std::max(stride * n_scenes, std::max((size_t)ctx->costmap_stride, n * sizeof(float)));
+	if ((rc = ctx->h_stage.ensure(stage))) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	unsigned char* hs = (unsigned char*)ctx->h_stage.p;
+	std::memset(hs, 0, stride * n_scenes);
+	for (int s = 0; s < n_scenes; ++s) {
+		pack_scene(ctx, worlds[s], highest_valid_cost_prev ? highest_valid_cost_prev + 4 * (size_t)s : nullptr, D.dt_d,
+		           hs + stride * s);
+	}
+	CU(cudaMemcpyAsync(ctx->d_scenes.p, hs, stride * n_scenes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (cells) {
+		CU(cudaMemcpy2DAsync(ctx->d_costmaps.p, ctx->costmap_stride, cells, n, n, n_scenes, cudaMemcpyHostToDevice, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	} else if (n_scenes > 1) {
+		set_err("hmp_plan_batch needs per-scene costmap cells");
+		return HMP_E_INVALID;
+	}
+	if (any_grid) {
+		float* f = (float*)hs;
+		for (int s = 0; s < n_scenes; ++s) {
+			for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+				if (!target_dist[g]) {
+					set_err("target_dist[%d] is null", g);
+					return HMP_E_INVALID;
+				}
+				const double* src = target_dist[g] + (size_t)s * n;
+				for (size_t i = 0; i < n; ++i) f[i] = (float)src[i];
+				CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + ((size_t)s * HMP_NUM_MAPGRIDS + g) * n, f, n * sizeof(float),
+				                   cudaMemcpyHostToDevice, ctx->stream));
+				CU(cudaStreamSynchronize(ctx->stream));
+			}
+		}
+		for (bool& b : ctx->have_grid) b = true;
+	}
+	PlanLaunch pl{n_scenes, (uint32_t)stride, 0, T};
+	return run_cycle(ctx, D, amp_table, nullptr, 0, pl, results, nullptr, 0);
+}
+
+// Re-runs the selection of the last plan on the data still resident on the device (no host<->device
+// traffic except the 16-byte result): used to time the kernels with inputs already in HBM.
+int hmp_replan_resident(HmpContext* ctx, HmpResult* results) {
+	if (!ctx || !results || !ctx->last_valid) {
+		set_err("no previous plan to re-run");
+		return HMP_E_NOT_READY;
+	}
+	CU(cudaSetDevice(ctx->device));
+	PlanLaunch pl{ctx->last_n_scenes, ctx->last_scene_stride, (int)ctx->last_extra.size(), ctx->last_T};
+	return run_cycle(ctx, ctx->last_dev_params, ctx->last_amp_table, pl.n_extra ? ctx->last_extra.data() : nullptr, pl.n_extra,
+	                 pl, results, nullptr, 0);
+}
+
+int hmp_get_explored_totals(HmpContext* ctx, double* totals, int32_t n) {
+	if (!ctx || !totals || !ctx->last_valid) {
+		set_err("no previous plan");
+		return HMP_E_NOT_READY;
+	}
+	if (n != ctx->last_n_candidates * ctx->last_n_scenes) {
+		set_err("n = %d, expected %d", n, ctx->last_n_candidates * ctx->last_n_scenes);
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(totals, ctx->d_totals.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return HMP_OK;
+}
+
+int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n, double* costs_out, double* seeds_out,
+                double* poses_out, int32_t* n_steps_out) {
+	if (!ctx || !candidate_indices || n <= 0 || !ctx->last_valid) {
+		set_err("no previous plan or bad arguments");
+		return HMP_E_NOT_READY;
+	}
+	if (ctx->last_n_scenes != 1) {
+		set_err("hmp_explain works on single-scene plans");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	const DevParams& D = ctx->last_dev_params;
+	const int T = D.T;
+	const size_t doubles = (size_t)n * (HMP_NUM_COSTS + 3 + (size_t)T * 3 + (size_t)T * 8);
+	const size_t bytes = doubles * sizeof(double) + (size_t)n * 2 * sizeof(int32_t);
+	int rc;
+	if ((rc = ctx->d_dbg.ensure(bytes))) return rc;
+	if ((rc = ctx->h_out.ensure(bytes))) return rc;
+	double* base = (double*)ctx->d_dbg.p;
+	int32_t* d_idx = (int32_t*)(base + doubles);
+	int32_t* d_np = d_idx + n;
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(d_idx, candidate_indices, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	const CtrlLayout cl = ctrl_layout(1);
+	unsigned char* ctrl = (unsigned char*)ctx->d_ctrl.p;
+	CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 4 * sizeof(unsigned int), st));
+	int blocks_x = 0, in_smem = 0;
+	size_t smem = 0;
+	PlanLaunch pl{1, ctx->last_scene_stride, 0, T};
+	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem))) return rc;
+	KernelArgs A;
+	std::memset(&A, 0, sizeof(A));
+	A.params = (const DevParams*)ctx->d_params.p;
+	A.amp_values = (const double*)ctx->d_amp.p;
+	A.extra_samples = (const double*)ctx->d_extra.p;
+	A.scenes = (const uint8_t*)ctx->d_scenes.p;
+	A.scene_stride = ctx->last_scene_stride;
+	A.n_scenes = 1;
+	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
+	A.costmap_stride = ctx->costmap_stride;
+	A.costmap_in_smem = in_smem;
+	A.mapgrids = (const float*)ctx->d_mapgrids.p;
+	A.cand_list = d_idx;
+	A.n_work = n;
+	A.counters = (unsigned int*)(ctrl + cl.off_counters);
+	A.hv_out = (unsigned int*)(ctrl + cl.off_hv);
+	A.best_out = (double*)(ctrl + cl.off_best);
+	A.d_costs = base;
+	A.d_seeds = A.d_costs + (size_t)n * HMP_NUM_COSTS;
+	A.d_poses = A.d_seeds + (size_t)n * 3;
+	A.d_forces = A.d_poses + (size_t)n * T * 3;
+	A.d_nposes = d_np;
+	int bx = (int)std::min<long long>(((long long)n + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, (long long)ctx->sm_count * 4);
+	CU(cudaMemsetAsync(base, 0, doubles * sizeof(double), st));
+	CU(hmp_dev_launch_plan(&A, bx, 1, smem, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(ctx->h_out.p, base, bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const double* h = (const double*)ctx->h_out.p;
+	if (costs_out) std::memcpy(costs_out, h, (size_t)n * HMP_NUM_COSTS * sizeof(double));
+	if (seeds_out) std::memcpy(seeds_out, h + (size_t)n * HMP_NUM_COSTS, (size_t)n * 3 * sizeof(double));
+	if (poses_out) std::memcpy(poses_out, h + (size_t)n * (HMP_NUM_COSTS + 3), (size_t)n * T * 3 * sizeof(double));
+	if (n_steps_out) std::memcpy(n_steps_out, (const int32_t*)(h + doubles) + n, (size_t)n * sizeof(int32_t));
+	return HMP_OK;
+}
+
+// Per-step forces of the candidates of the last hmp_explain call: [n][T][8] doubles
+// (internal.xy, dynamic.xy, static.xy, human-action.xy). Parity-test hook.
+int hmp_debug_last_forces(HmpContext* ctx, int32_t n, double* forces_out) {
+	if (!ctx || !forces_out || !ctx->last_valid || n <= 0) {
+		set_err("bad arguments");
+		return HMP_E_INVALID;
+	}
+	const int T = ctx->last_dev_params.T;
+	const double* h = (const double*)ctx->h_out.p;
+	std::memcpy(forces_out, h + (size_t)n * (HMP_NUM_COSTS + 3 + (size_t)T * 3), (size_t)n * T * 8 * sizeof(double));
+	return HMP_OK;
+}
+
+int hmp_num_steps(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_T : -1; }
+
+// ---- parity hooks ------------------------------------------------------------------------------------
+static int debug_params(HmpContext* ctx, DevParams& D) {
+	HmpSampling s;
+	for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) {
+		s.amp_min[a] = s.amp_max[a] = 1.0;
+		s.amp_granularity[a] = 1.0;
+	}
+	std::vector<double> amp;
+	int rc = build_dev_params(ctx, &s, 0, 1, D, amp);
+	if (rc) return rc;
+	if ((rc = ctx->d_params.ensure(sizeof(DevParams)))) return rc;
+	CU(cudaMemcpyAsync(ctx->d_params.p, &D, sizeof(D), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_debug_world_to_map(HmpContext* ctx, const double* wx, const double* wy, int32_t n, int32_t* mx, int32_t* my,
+                           int32_t* ok) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!wx || !wy || !mx || !my || !ok || n <= 0) {
+		set_err("bad arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	DevParams D;
+	if ((rc = debug_params(ctx, D))) return rc;
+	size_t bytes = (size_t)n * (2 * sizeof(double) + 3 * sizeof(int32_t));
+	if ((rc = ctx->d_dbg.ensure(bytes))) return rc;
+	double* dwx = (double*)ctx->d_dbg.p;
+	double* dwy = dwx + n;
+	int32_t* dmx = (int32_t*)(dwy + n);
+	int32_t* dmy = dmx + n;
+	int32_t* dok = dmy + n;
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(dwx, wx, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(dwy, wy, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_world_to_map((const DevParams*)ctx->d_params.p, dwx, dwy, n, dmx, dmy, dok, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(mx, dmx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(my, dmy, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(ok, dok, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return HMP_OK;
+}
+
+int hmp_debug_footprint_cost(HmpContext* ctx, const double* xyt, int32_t n, double* cost) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!xyt || !cost || n <= 0 || !ctx->have_footprint) {
+		set_err("bad arguments or footprint missing");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	DevParams D;
+	if ((rc = debug_params(ctx, D))) return rc;
+	size_t bytes = (size_t)n * 4 * sizeof(double);
+	if ((rc = ctx->d_dbg.ensure(bytes))) return rc;
+	double* dx = (double*)ctx->d_dbg.p;
+	double* dc = dx + 3 * (size_t)n;
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(dx, xyt, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_footprint_cost((const DevParams*)ctx->d_params.p, (const uint8_t*)ctx->d_costmaps.p, dx, n, dc, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(cost, dc, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return HMP_OK;
+}
+
+// fuzz::Processor::process on the device for n input tuples (dir_alpha, dir_beta, rel_loc, dist_angle);
+// out: (value, membership) per tuple.
+int hmp_debug_fis(HmpContext* ctx, const double* in4, int32_t n, double* out2) {
+	if (!ctx || !in4 || !out2 || n <= 0) {
+		set_err("bad arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	int rc;
+	if ((rc = ctx->d_dbg.ensure((size_t)n * 6 * sizeof(float)))) return rc;
+	std::vector<float> hin((size_t)n * 4), hout((size_t)n * 2);
+	for (size_t i = 0; i < hin.size(); ++i) hin[i] = (float)in4[i];
+	float* din = (float*)ctx->d_dbg.p;
+	float* dout = din + (size_t)n * 4;
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(din, hin.data(), hin.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_fis(din, n, dout, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(hout.data(), dout, hout.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	for (size_t i = 0; i < hout.size(); ++i) out2[i] = hout[i];
+	return HMP_OK;
+}
+
+int64_t hmp_launch_count(HmpContext* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

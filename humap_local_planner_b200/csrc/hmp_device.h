@@ -15,6 +15,8 @@
 #include "../../include/hmp_planner.h"
 
 #define HMP_DEV_MAX_KERNEL_PTS 9   /* centre + 8 offsets (RECTANGLE kernel) */
+#define HMP_WARPS_PER_BLOCK 8
+#define HMP_THREADS_PER_BLOCK (32 * HMP_WARPS_PER_BLOCK)
 
 /* Rollout-invariant record of one object treated with the STATIC interaction formulation
  * (reference StaticObject, world.h:24-41). d0 = object point - robot-side point at t = 0; during the
@@ -37,10 +39,11 @@ struct DevDynamic {
 /* humap_local_planner::Person prediction source (person.h, trajectory.h:160-193) + covariances +
  * the speed-dependent personal-space variances (personal_space_intrusion_cost_function.cpp:55-58). */
 struct DevPerson {
-	float x, y, yaw, _p0;      /* pose at t = 0, robot-centred frame */
-	float vx, vy, vth, _p1;
-	float cxx, cxy, cyx, cyy;
-	float var_front, var_rear, var_side, _p2;
+	float x, y, yaw, vth;      /* pose at t = 0 in the robot-centred frame, yaw rate     */
+	float vx, vy, cos0, sin0;  /* velocity (global), cos/sin of yaw at t = 0             */
+	float cxx, cxy, cyx, cyy;  /* position covariance                                    */
+	float var_front, var_rear, var_side;
+	float radius_eff;          /* person_model_radius + sqrt((cxx + cyy) / 2), heading-disturbance occupancy circle */
 };
 
 /* Group: static over the horizon (group.h:18-21) so the inverse covariance of the O-space Gaussian
@@ -52,7 +55,7 @@ struct DevGroup {
 };
 
 /* Per-scene header. Arrays follow in one blob; offsets are in bytes from the blob start. */
-struct DevScene {
+struct alignas(16) DevScene {
 	double x0, y0, yaw0;          /* robot pose at t = 0 (absolute, map frame)                         */
 	float u0x, u0y, u0w;          /* robot global velocity at t = 0 (computeVelocityGlobal(vel_, pose_)) */
 	float vlx, vly, vlw;          /* vel_: current base-frame velocity (smoothness critics)            */
@@ -71,11 +74,12 @@ struct DevScene {
 
 /* Flattened HumapConfig for the device: FP32 where the arithmetic is FP32, FP64 where the reference's
  * doubles decide an integer (cell index) or the final weighted sum. */
-struct DevParams {
+struct alignas(16) DevParams {
 	/* --- time discretisation (social_trajectory_generator.cpp:324-328) */
 	int32_t T;                    /* num_steps                                      */
 	int32_t n_ttc_extra;          /* iterations of the TTC look-ahead loop (ttc_cost_function.cpp:100) */
 	double dt_d;                  /* sim_time / T                                   */
+	double ttc_rollout_time_d;
 	float dt;
 	float people_dt;
 	/* --- limits */
@@ -89,9 +93,9 @@ struct DevParams {
 	int32_t fov_method, filter_forces, disable_interaction;
 	float mass, m_over_tau;
 	float k_int, k_stat, k_dyn, min_force, max_force;
-	float fov_sigma;              /* Gaussian sigma = cfg.fov (variance (2 fov / 2)^2) */
-	float fov_gauss_scale;        /* 1 / (sigma sqrt(2 pi))                            */
-	float fov_neg_inv_2var;       /* -1 / (2 sigma^2)                                  */
+	float fov_half;               /* linear method: half angle = cfg.fov                */
+	float fov_gauss_scale;        /* 1 / (sigma sqrt(2 pi)), sigma = cfg.fov            */
+	float fov_neg_inv_2var;       /* -1 / (2 sigma^2)                                   */
 	float base[9];                /* (float)cfg.{speed_desired, an, bn, cn, ap, bp, cp, aw, bw}: SFM float members */
 	/* --- FIS */
 	int32_t fis_on, fis_fov_method;
@@ -117,14 +121,13 @@ struct DevParams {
 	int32_t mg_stop_on_failure[HMP_NUM_MAPGRIDS];
 	int32_t mg_kernel[HMP_NUM_MAPGRIDS];
 	int32_t _padc;
-	double mg_xshift[HMP_NUM_MAPGRIDS], mg_yshift[HMP_NUM_MAPGRIDS], mg_mult[HMP_NUM_MAPGRIDS];
+	double mg_xshift[HMP_NUM_MAPGRIDS], mg_yshift[HMP_NUM_MAPGRIDS];
 	float unsat_max_trans, unsat_max_x, unsat_max_y;
 	float backward_penalty;
-	float ttc_collision_distance, ttc_rollout_time;
-	float hd_person_radius, hd_neg_inv_2var_fov, hd_dmin, hd_inv_max_speed;
+	float ttc_collision_distance, _padf;
+	float hd_neg_inv_2var_fov, hd_dmin, hd_inv_max_speed;
 	float ps_min_dist, ps_inv_max_speed;
 	int32_t unsat_whole, hd_whole, psi_whole, fsi_whole, ps_whole;
-	int32_t _pade;
 };
 
 /* Kernel argument block (passed by value). */
@@ -139,21 +142,21 @@ struct KernelArgs {
 	uint32_t costmap_stride;
 	int32_t costmap_in_smem;
 	const float* mapgrids;           /* [n_scenes][4][size_y * size_x]                            */
-	const float* fis_table;          /* [100][12]: x_i, mu_k(x_i) k = 0..10                       */
 	/* selection */
 	const int32_t* cand_list;        /* explicit candidate indices (detail mode) or null          */
 	int32_t n_work;                  /* candidates per scene to evaluate                          */
-	int32_t _pad;
+	int32_t use_best_index;          /* detail mode: candidate = (int)best_out[scene][1]          */
 	double* totals;                  /* [n_scenes][n_candidates] or null                          */
-	unsigned long long* block_best;  /* scratch [n_scenes][gridDim.x] x 2 (cost bits, index)      */
-	unsigned int* counters;          /* [n_scenes][4]: ticket, n_generated, n_valid, pad          */
-	float* hv_out;                   /* [n_scenes][4] highest_valid_cost (float bits, atomicMax)  */
+	unsigned long long* block_best;  /* scratch [n_scenes][gridDim.x][2] (cost bits, index)       */
+	unsigned int* counters;          /* [n_scenes][4]: work ticket, done ticket, n_generated, n_valid */
+	unsigned int* hv_out;            /* [n_scenes][4] highest_valid_cost (float bits, atomicMax)  */
 	double* best_out;                /* [n_scenes][2]: best total, best index (as double)         */
 	/* detail outputs (DETAIL kernel only) */
 	double* d_costs;                 /* [n_work][14]                                               */
 	double* d_seeds;                 /* [n_work][3]                                                */
 	double* d_poses;                 /* [n_work][T][3]                                             */
 	double* d_forces;                /* [n_work][T][8] or null                                     */
+	int32_t* d_nposes;               /* [n_work] poses recorded (T, or fewer when the generator rejected) */
 };
 
 #endif

@@ -250,7 +250,8 @@ typedef struct HmpResult {
 	double time_delta;             /* traj.time_delta_                                                         */
 	double amplifiers[HMP_NUM_AMPLIFIERS];  /* the winner's SampleAmplifierSet                                */
 	double highest_valid_cost[HMP_NUM_MAPGRIDS];  /* highest_valid_cost_ after the cycle (map_grid_cost_function.cpp:87,135) */
-	double gpu_ms;                 /* device time of the cycle (CUDA events), milliseconds                       */
+	double gpu_ms;                 /* device time of the cycle (CUDA events on the launching stream), milliseconds */
+	double gpu_ms_select;          /* ... of the rollout + scoring + selection kernel alone                        */
 } HmpResult;
 
 typedef struct HmpContext HmpContext;
@@ -297,6 +298,11 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes,
                    const double* highest_valid_cost_prev /* [n_scenes][4] or NULL */,
                    const HmpSampling* sampling, HmpResult* results);
 
+/* Re-runs the last hmp_plan / hmp_plan_batch on the scene data still resident in device memory (only
+ * the few-KB parameter block is re-sent and the result read back). No reference counterpart: it exists so
+ * that benchmarks can time the kernels with inputs already in HBM. */
+int hmp_replan_resident(HmpContext* ctx, HmpResult* results);
+
 /* ---- diagnostics of the LAST hmp_plan (traj_explored_, humap_planner.cpp:1367,1969-2084) ------ */
 /* Weighted total per candidate (negative = reference error code); n must equal n_candidates. */
 int hmp_get_explored_totals(HmpContext* ctx, double* totals, int32_t n);
@@ -313,6 +319,15 @@ int hmp_debug_world_to_map(HmpContext* ctx, const double* wx, const double* wy, 
                            int32_t* mx, int32_t* my, int32_t* ok);
 /* CostmapModel::footprintCost on the device for n poses (x, y, yaw) with the configured footprint. */
 int hmp_debug_footprint_cost(HmpContext* ctx, const double* xyt, int32_t n, double* cost);
+
+/* fuzz::Processor::process (src/fuzz/processor.cpp:200-271) on the device for n tuples
+ * (dir_alpha, dir_beta, rel_loc, dist_angle); out2 = (crisp direction, membership of the winning term). */
+int hmp_debug_fis(HmpContext* ctx, const double* in4, int32_t n, double* out2);
+/* Per-step forces of the candidates of the last hmp_explain call: [n][T][8] doubles
+ * (internal.xy, dynamic.xy, static.xy, human-action.xy), social_trajectory_generator.cpp:701-704. */
+int hmp_debug_last_forces(HmpContext* ctx, int32_t n, double* forces_out);
+/* Rollout steps of the last plan (SocialTrajectoryGenerator::computeStepsNumber), -1 if none. */
+int hmp_num_steps(HmpContext* ctx);
 
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t hmp_launch_count(HmpContext* ctx);

@@ -1,0 +1,137 @@
+"""ctypes binding of the CPU oracle (oracle/hmp_oracle.cpp). TEST INFRASTRUCTURE: only tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from humap_local_planner_b200.capi import (HmpParams, HmpWorld, HmpSampling, HmpSample, HmpResult, NUM_COSTS,
+                                           NUM_MAPGRIDS, NUM_AMPLIFIERS, Scene)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = os.path.join(ROOT, "oracle", "_build", "libhmp_oracle.so")
+_d, _i = C.c_double, C.c_int32
+_lib = None
+
+
+class OrcPlanInput(C.Structure):
+    _fields_ = [
+        ("params", C.POINTER(HmpParams)), ("world", C.POINTER(HmpWorld)), ("sampling", C.POINTER(HmpSampling)),
+        ("extra", C.c_void_p), ("n_extra", _i),
+        ("size_x", _i), ("size_y", _i), ("cells", C.c_void_p),
+        ("origin_x", _d), ("origin_y", _d), ("resolution", _d),
+        ("target_dist", C.c_void_p * NUM_MAPGRIDS), ("highest_valid_cost_prev", _d * NUM_MAPGRIDS),
+        ("footprint_xy", C.c_void_p), ("n_footprint", _i),
+        ("early_exit", _i), ("cand_begin", _i), ("cand_end", _i),
+    ]
+
+
+class OrcPlanOutput(C.Structure):
+    _fields_ = [
+        ("result", HmpResult),
+        ("totals", C.c_void_p), ("costs", C.c_void_p), ("seeds", C.c_void_p), ("poses", C.c_void_p),
+        ("n_poses", C.c_void_p), ("generated", C.c_void_p), ("best_poses", C.c_void_p), ("forces", C.c_void_p),
+        ("forces_candidate", _i), ("_pad", _i),
+    ]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        _lib = C.CDLL(_LIB)
+        _lib.orc_plan.argtypes = [C.POINTER(OrcPlanInput), C.POINTER(OrcPlanOutput)]
+        _lib.orc_plan.restype = C.c_int
+        _lib.orc_num_candidates.argtypes = [C.POINTER(HmpSampling), C.c_int]
+        _lib.orc_num_steps.argtypes = [C.POINTER(HmpParams), C.POINTER(HmpWorld)]
+        for name, res in (("orc_wrap", _d), ("orc_yaw_roundtrip", _d), ("orc_factor_fov", _d),
+                          ("orc_behaviour_strength_exp", _d), ("orc_passing_speed", _d), ("orc_direction", _d),
+                          ("orc_len3", _d), ("orc_theta_alpha_beta_2011", _d), ("orc_theta_alpha_beta_2014", _d),
+                          ("orc_relative_speed", _d), ("orc_personal_space", _d), ("orc_formation_space", _d),
+                          ("orc_heading_disturbance", _d)):
+            getattr(_lib, name).restype = res
+        _lib.orc_wrap.argtypes = [_d]
+        _lib.orc_yaw_roundtrip.argtypes = [_d]
+        _lib.orc_factor_fov.argtypes = [_d, _d, C.c_int]
+        _lib.orc_behaviour_strength_exp.argtypes = [_d, _d, _d, _d]
+        _lib.orc_passing_speed.argtypes = [_d, _d, _d, _d]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def num_candidates(sampling: HmpSampling, n_extra: int = 0) -> int:
+    return lib().orc_num_candidates(C.byref(sampling), n_extra)
+
+
+def num_steps(params: HmpParams, world: HmpWorld) -> int:
+    return lib().orc_num_steps(C.byref(params), C.byref(world))
+
+
+def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, early_exit: bool = False,
+         cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1):
+    """Runs orc_plan and returns a dict of numpy arrays (+ 'result': HmpResult)."""
+    L = lib()
+    ex = None
+    n_extra = 0
+    if extra is not None:
+        ex = np.ascontiguousarray(extra, dtype=np.float64).reshape(-1, NUM_AMPLIFIERS)
+        n_extra = ex.shape[0]
+    Cn = num_candidates(sampling, n_extra)
+    T = num_steps(params, scene.world)
+    inp = OrcPlanInput()
+    inp.params = C.pointer(params)
+    inp.world = C.pointer(scene.world)
+    inp.sampling = C.pointer(sampling)
+    inp.extra = _p(ex)
+    inp.n_extra = n_extra
+    inp.size_x, inp.size_y = scene.size_x, scene.size_y
+    inp.cells = _p(scene.cells)
+    inp.origin_x, inp.origin_y, inp.resolution = scene.origin_x, scene.origin_y, scene.resolution
+    for g in range(NUM_MAPGRIDS):
+        inp.target_dist[g] = scene.grids[g].ctypes.data
+        inp.highest_valid_cost_prev[g] = scene.hv_prev[g]
+    inp.footprint_xy = _p(scene.footprint)
+    inp.n_footprint = scene.footprint.shape[0]
+    inp.early_exit = 1 if early_exit else 0
+    inp.cand_begin, inp.cand_end = cand_range
+    out = OrcPlanOutput()
+    arrs = {}
+    if "totals" in want:
+        arrs["totals"] = np.full(Cn, np.nan)
+        out.totals = _p(arrs["totals"])
+    if "costs" in want:
+        arrs["costs"] = np.full((Cn, NUM_COSTS), np.nan)
+        out.costs = _p(arrs["costs"])
+    if "seeds" in want:
+        arrs["seeds"] = np.zeros((Cn, 3))
+        out.seeds = _p(arrs["seeds"])
+    if "poses" in want:
+        arrs["poses"] = np.zeros((Cn, T, 3))
+        out.poses = _p(arrs["poses"])
+    if "n_poses" in want:
+        arrs["n_poses"] = np.zeros(Cn, dtype=np.int32)
+        out.n_poses = _p(arrs["n_poses"])
+    if "generated" in want:
+        arrs["generated"] = np.zeros(Cn, dtype=np.int32)
+        out.generated = _p(arrs["generated"])
+    arrs["best_poses"] = np.zeros((T, 3))
+    out.best_poses = _p(arrs["best_poses"])
+    out.forces_candidate = forces_candidate
+    if forces_candidate >= 0:
+        arrs["forces"] = np.zeros((T, 8))
+        out.forces = _p(arrs["forces"])
+    rc = L.orc_plan(C.byref(inp), C.byref(out))
+    assert rc == 0
+    res = HmpResult()
+    C.memmove(C.byref(res), C.byref(out.result), C.sizeof(HmpResult))
+    arrs["result"] = res
+    arrs["T"] = T
+    arrs["C"] = Cn
+    return arrs
