@@ -547,7 +547,7 @@ HmpContext* hmp_create(int device_id) {
 	}
 	ctx->device = device_id;
 	ctx->sm_count = prop.multiProcessorCount;
-	ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
 	    cudaEventCreate(&ctx->evm) != cudaSuccess ||
