@@ -1920,6 +1920,45 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	return 0;
 }
 
+// Scores ONE externally supplied trajectory (poses [n][3], seed twist, dt = sim_time / steps) with all critics
+// in the reference order, no early exit: used to check the CUDA critics on the CUDA path's own poses.
+int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, const double seed[3], double* raw_costs,
+                         double* total, double* hv_out) {
+	PlanState st;
+	st.P = in->params;
+	st.cm = Costmap{in->cells, in->size_x, in->size_y, in->origin_x, in->origin_y, in->resolution};
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		MapGridCritic& m = st.grids[g];
+		m.target_dist = in->target_dist[g];
+		m.size_x = in->size_x;
+		m.size_y = in->size_y;
+		m.xshift = in->params->costs.xshift[g];
+		m.yshift = in->params->costs.yshift[g];
+		m.stop_on_failure = in->params->costs.stop_on_failure[g] != 0;
+		m.n_kernel_size = in->params->costs.neighbour_kernel_size[g];
+		m.n_cost_multiplier = in->params->costs.neighbour_cost_multiplier[g];
+		m.highest_valid_cost_prev = in->highest_valid_cost_prev[g];
+		m.highest_valid_cost = 0.0;
+	}
+	st.footprint.assign(in->footprint_xy, in->footprint_xy + 2 * in->n_footprint);
+	buildScene(st, *in->params, *in->world);
+	BlpTrajectory traj;
+	traj.xv = seed[0];
+	traj.yv = seed[1];
+	traj.thetav = seed[2];
+	traj.time_delta = in->params->general.sim_time / orc_num_steps(in->params, in->world);
+	for (int i = 0; i < n; ++i) {
+		traj.x.push_back(poses[3 * i]);
+		traj.y.push_back(poses[3 * i + 1]);
+		traj.th.push_back(poses[3 * i + 2]);
+	}
+	*total = scoreTrajectoryAll(st, traj, -1.0, false, raw_costs);
+	if (hv_out) {
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) hv_out[g] = st.grids[g].highest_valid_cost;
+	}
+	return 0;
+}
+
 // ---- known-answer-test hooks (reference test/*.cpp), thin wrappers over the restated functions ----
 double orc_wrap(double a) { return wrap(a); }
 double orc_yaw_roundtrip(double yaw) { return yaw_roundtrip(yaw); }

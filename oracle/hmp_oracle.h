@@ -51,6 +51,8 @@ typedef struct OrcPlanOutput {
 } OrcPlanOutput;
 
 int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out);
+int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, const double seed[3], double* raw_costs,
+                         double* total, double* hv_out);
 int orc_num_candidates(const HmpSampling* sampling, int n_extra);
 int orc_num_steps(const HmpParams* P, const HmpWorld* w);
 int orc_samples(const HmpSampling* sampling, const HmpSample* extra, int n_extra, HmpSample* out);

@@ -74,17 +74,7 @@ def num_steps(params: HmpParams, world: HmpWorld) -> int:
     return lib().orc_num_steps(C.byref(params), C.byref(world))
 
 
-def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, early_exit: bool = False,
-         cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1):
-    """Runs orc_plan and returns a dict of numpy arrays (+ 'result': HmpResult)."""
-    L = lib()
-    ex = None
-    n_extra = 0
-    if extra is not None:
-        ex = np.ascontiguousarray(extra, dtype=np.float64).reshape(-1, NUM_AMPLIFIERS)
-        n_extra = ex.shape[0]
-    Cn = num_candidates(sampling, n_extra)
-    T = num_steps(params, scene.world)
+def _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range):
     inp = OrcPlanInput()
     inp.params = C.pointer(params)
     inp.world = C.pointer(scene.world)
@@ -101,6 +91,36 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     inp.n_footprint = scene.footprint.shape[0]
     inp.early_exit = 1 if early_exit else 0
     inp.cand_begin, inp.cand_end = cand_range
+    return inp
+
+
+def score_trajectory(params: HmpParams, scene: Scene, sampling: HmpSampling, poses: np.ndarray, seed):
+    """All critics of the oracle on an externally supplied trajectory. Returns (raw costs[14], total, hv[4])."""
+    L = lib()
+    L.orc_score_trajectory.argtypes = [C.POINTER(OrcPlanInput), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    inp = _make_input(params, scene, sampling, None, 0, False, (0, 0))
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 3)
+    sd = np.ascontiguousarray(seed, dtype=np.float64)
+    raw = np.zeros(NUM_COSTS)
+    total = np.zeros(1)
+    hv = np.zeros(NUM_MAPGRIDS)
+    L.orc_score_trajectory(C.byref(inp), _p(poses), poses.shape[0], _p(sd), _p(raw), _p(total), _p(hv))
+    return raw, float(total[0]), hv
+
+
+def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, early_exit: bool = False,
+         cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1):
+    """Runs orc_plan and returns a dict of numpy arrays (+ 'result': HmpResult)."""
+    L = lib()
+    ex = None
+    n_extra = 0
+    if extra is not None:
+        ex = np.ascontiguousarray(extra, dtype=np.float64).reshape(-1, NUM_AMPLIFIERS)
+        n_extra = ex.shape[0]
+    Cn = num_candidates(sampling, n_extra)
+    T = num_steps(params, scene.world)
+    inp = _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range)
     out = OrcPlanOutput()
     arrs = {}
     if "totals" in want:
@@ -135,3 +155,33 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     arrs["T"] = T
     arrs["C"] = Cn
     return arrs
+
+
+def plan_sampled(params, scene, sampling, indices):
+    """Oracle results for an explicit list of candidate indices (one orc_plan call per candidate)."""
+    out = {"totals": [], "costs": [], "poses": [], "seeds": [], "n_poses": []}
+    for i in indices:
+        r = plan(params, scene, sampling, cand_range=(int(i), int(i) + 1))
+        for k in out:
+            out[k].append(r[k][int(i)])
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def plan_all_threaded(params, scene, sampling, n_threads=None, want=("totals",)):
+    """Full-grid oracle totals, split over host threads (ctypes releases the GIL during orc_plan)."""
+    import concurrent.futures as cf
+    import os as _os
+    Cn = num_candidates(sampling)
+    n_threads = n_threads or min(64, _os.cpu_count() or 1)
+    bounds = np.linspace(0, Cn, n_threads * 4 + 1).astype(int)
+    totals = np.full(Cn, np.nan)
+
+    def work(k):
+        a, b = int(bounds[k]), int(bounds[k + 1])
+        if b > a:
+            r = plan(params, scene, sampling, cand_range=(a, b), want=("totals",))
+            totals[a:b] = r["totals"][a:b]
+
+    with cf.ThreadPoolExecutor(n_threads) as ex_:
+        list(ex_.map(work, range(len(bounds) - 1)))
+    return totals

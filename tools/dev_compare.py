@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--n", type=int, default=72, help="candidates compared against the oracle")
     ap.add_argument("--fis", type=int, default=1)
     ap.add_argument("--forces", type=int, default=-1)
+    ap.add_argument("--worst", type=int, default=0)
     a = ap.parse_args()
     cfg = scenes.CONFIGS[a.cfg]
     sc = scenes.make_scene(cfg, a.seed)
@@ -63,6 +64,17 @@ def main():
     perr[..., 2] = np.abs((perr[..., 2] + np.pi) % (2 * np.pi) - np.pi)
     if gen.any():
         print(f"pose err: max xy {perr[..., :2].max():.3e} max yaw {perr[..., 2].max():.3e}; frac cands > 1e-4: {(perr.max(axis=(1,2)) > 1e-4).mean():.4f}")
+    if gen.any() and a.worst:
+        gi = np.where(gen)[0]
+        w = gi[np.argmax(perr.max(axis=(1, 2)))]
+        ci = int(idx[w])
+        r = ob.plan(params, sc, smp, cand_range=(ci, ci + 1), forces_candidate=ci)
+        pe = np.abs(ex["poses"][w] - r["poses"][ci])
+        df = ex["forces"][w] - r["forces"]
+        print(f"worst candidate {ci}: per-step [pose err xy, yaw | dF int, dyn, stat, human | F gpu dyn, stat, human]")
+        for i in range(T):
+            print(f"  {i:2d} {pe[i,:2].max():.2e} {pe[i,2]:.2e} | {np.abs(df[i,0:2]).max():.2e} {np.abs(df[i,2:4]).max():.2e} {np.abs(df[i,4:6]).max():.2e} {np.abs(df[i,6:8]).max():.2e} | "
+                  f"{np.hypot(*ex['forces'][w][i,2:4]):.3f} {np.hypot(*ex['forces'][w][i,4:6]):.3f} {np.hypot(*ex['forces'][w][i,6:8]):.3f}")
     for k, name in enumerate(COST_NAMES):
         g, o = ex["costs"][:, k], o_costs[:, k]
         m = np.isfinite(g) & np.isfinite(o)
