@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the trajectory sampling + scoring hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg cfg2]
+
+A "step" is one planning cycle: every candidate of the workload rolled out, scored by all critics and the
+argmin selected. The default workload is BASELINE.json configs[2] ("crowd stress": 65 536 candidates x
+50 people x 8 F-formation groups x 500 obstacle points, 5 s horizon) -- the configuration the metric's
+"p50 planning-cycle latency at 64k candidates" is quoted on; it fits one GPU.
+
+  value  candidates/s with the scene already resident in HBM (hmp_replan_resident), timed with CUDA events
+         on the library's launching stream (HmpResult.gpu_ms), max over ranks.
+  e2e    the same metric through the public C-ABI calls a planner makes every cycle, host buffers in, host
+         result out: hmp_set_costmap + 4 x hmp_set_mapgrid + hmp_set_footprint + hmp_plan (wall clock).
+  N > 1  independent scenes, one per rank (scene seed = rank), no collective on the data path: weak scaling.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, FP64, all host threads) on a
+bounded candidate sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "candidate trajectories scored/sec"
+UNIT = "candidates/s"
+
+
+def algorithmic_flops_per_candidate(cfg, params, n_static, n_dynamic, fis_on, T, K=8, V=16, c_cells=45):
+    """W = 294 + 86 S + 103 D + 185 P + 45 G + (K+1)(16 V + 6 c) [+ 2900 D with FIS] per step."""
+    P, G = cfg.n_people, cfg.n_groups
+    W = 294 + 86 * n_static + 103 * n_dynamic + 185 * P + 45 * G + (K + 1) * (16 * V + 6 * c_cells)
+    if fis_on:
+        W += 2900 * n_dynamic
+    return T * W + 60, W
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        smax = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if "Active" in r[3 + i] and "Not" not in r[3 + i]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(cfg, scene, params, sampling, seconds_budget=12.0):
+    """The oracle (CPU restatement of the reference path) on a bounded sample, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    import concurrent.futures as cf
+    cores = os.cpu_count() or 1
+    Cn = ob.num_candidates(sampling)
+    # calibrate on a few candidates, then size the sample for ~seconds_budget of wall time
+    probe = np.unique(np.linspace(0, Cn - 1, 4).astype(int))
+    t0 = time.perf_counter()
+    for i in probe:
+        ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",))
+    per = (time.perf_counter() - t0) / len(probe)
+    n = int(min(Cn, max(cores, seconds_budget / per * cores)))
+    idx = np.unique(np.linspace(0, Cn - 1, n).astype(int))
+    chunks = np.array_split(idx, cores * 2)
+
+    def work(ch):
+        for i in ch:
+            ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",))
+        return len(ch)
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(cores) as ex:
+        done = sum(ex.map(work, chunks))
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} of {Cn} candidates of {cfg.name} (evenly spaced over the sampling grid), {dt:.1f} s wall, "
+                      f"single-thread rate {1.0 / per:.1f} candidates/s"}, dt, done
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the CPU restatement of the reference path, bounded sample per step, rank 0 only."""
+    if rank != 0:
+        return
+    from humap_local_planner_b200 import scenes
+    cfg = scenes.CONFIGS[args.cfg]
+    scene = scenes.make_scene(cfg, 0)
+    params = scenes.make_params(cfg, fis=bool(args.fis))
+    sampling = scenes.make_sampling(cfg)
+    per_step = max(3.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    times, counts = [], []
+    base = None
+    for s in range(args.warmup + args.steps):
+        base, dt, done = cpu_baseline(cfg, scene, params, sampling, seconds_budget=per_step)
+        if s >= args.warmup:
+            times.append(dt)
+            counts.append(done)
+    value = sum(counts) / sum(times)
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": _workload_name(cfg, args), "candidates_per_step_sample": int(np.mean(counts))},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def _workload_name(cfg, args):
+    return (f"{cfg.name}: {cfg.n_people} people, {cfg.n_groups} F-formation groups, {cfg.n_obstacles} obstacle points, "
+            f"{cfg.size}x{cfg.size} costmap @ {cfg.resolution} m, horizon {cfg.sim_time} s @ {cfg.sim_granularity} s, "
+            f"FIS {'on' if args.fis else 'off'}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="cfg2")
+    ap.add_argument("--fis", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from humap_local_planner_b200 import Planner, scenes
+    from humap_local_planner_b200.sharding import scenes_for_rank
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = scenes.CONFIGS[args.cfg]
+    # independent scenes are sharded over ranks (scene s -> rank s mod N), one scene per rank per step: weak scaling
+    my_scene_ids = scenes_for_rank(world, rank, world)
+    scene = scenes.make_scene(cfg, seed=my_scene_ids[0])
+    params = scenes.make_params(cfg, fis=bool(args.fis))
+    sampling = scenes.make_sampling(cfg)
+    pl = Planner(local_rank)
+    pl.set_params(params)
+
+    def full_cycle():
+        # what HumapPlanner does every control cycle before and at the seam (humap_planner.cpp:1054-1141, :1294-1377)
+        pl.set_costmap(scene.cells, scene.origin_x, scene.origin_y, scene.resolution)
+        for g in range(4):
+            pl.set_mapgrid(g, scene.grids[g], scene.hv_prev[g])
+        pl.set_footprint(scene.footprint)
+        return pl.plan(scene.world, sampling, want_poses=True)
+
+    res, _ = full_cycle()
+    C = res.n_candidates
+    T = pl.num_steps()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- value: inputs resident in HBM, CUDA-event time of the kernels on the launching stream ------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        pl.replan_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pl.launch_count()
+    dev_ms, sel_ms = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()          # L2 flush between timed iterations (not inside the event-timed region)
+        torch.cuda.synchronize()
+        r = pl.replan_resident()[0]
+        dev_ms.append(r.gpu_ms)
+        sel_ms.append(r.gpu_ms_select)
+    barrier()
+    wall_resident = time.perf_counter() - t_wall0
+    launches = pl.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = torch.tensor([sum(dev_ms) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_dev = float(t_dev.item())
+
+    # ---- e2e: host buffers through the public C-ABI, every step uploads the cycle's inputs and reads the result ----
+    for _ in range(2):
+        full_cycle()
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r, poses = full_cycle()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    t_e2e = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+
+    if rank == 0:
+        import ctypes as Cc
+        from humap_local_planner_b200 import capi
+        n_cells = scene.cells.size
+        h2d = n_cells + 4 * n_cells * 4 + Cc.sizeof(capi.HmpParams) + scene.world.n_obstacles * 64 + scene.world.n_people * 64 + \
+            scene.world.n_groups * 32 + 10 * 64 * 8
+        d2h = (14 + 3 + 3 * T + 1) * 8 + 8 + 64
+        nd = sum(1 for i in range(scene.world.n_obstacles) if scene.world.obstacles[i].force_dynamic or
+                 (scene.world.obstacles[i].vx ** 2 + scene.world.obstacles[i].vy ** 2) ** 0.5 > 0.035)
+        ns = scene.world.n_obstacles - nd
+        flops_cand, W = algorithmic_flops_per_candidate(cfg, params, ns, nd, bool(args.fis), T)
+        sel_s = statistics.mean(sel_ms) * 1e-3
+        achieved = C * flops_cand / sel_s / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        peak_fp32 = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": world * C * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload_name(cfg, args), "candidates": C, "steps_per_rollout": T,
+                       "parallelism": f"independent scenes x{world}, one per rank, no collective",
+                       "l2": "flushed with a 256 MiB write between timed iterations", "timing": "CUDA events on the launching stream"},
+            "p50_cycle_ms": statistics.median(dev_ms), "p99_cycle_ms": sorted(dev_ms)[min(len(dev_ms) - 1, int(0.99 * len(dev_ms)))],
+            "p50_cycle_ms_e2e": 1e3 * statistics.median(e2e_times),
+            "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
+            "e2e": {"value": world * C * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32-cuda-core", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s",
+                         "frac": achieved / peak_fp32, "traffic": None,
+                         "note": f"algorithmic flop per candidate-step W={W} (SURVEY.md 8d formula), per candidate T*W+60; dominant kernel "
+                                 f"plan_kernel<false,float> avg {1e3 * sel_s:.3f} ms; peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz "
+                                 "(MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is not HBM- or tensor-bound)"},
+            "best_index": int(r.best_index), "best_total": float(r.best_total), "n_valid": int(r.n_valid),
+        }
+        if not args.no_cpu_baseline:
+            base, _, _ = cpu_baseline(cfg, scene, params, sampling, seconds_budget=12.0)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    pl.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

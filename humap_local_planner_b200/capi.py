@@ -118,7 +118,7 @@ ABI_SYMBOLS = (
     "hmp_create", "hmp_destroy", "hmp_last_error", "hmp_abi_version", "hmp_set_params", "hmp_set_costmap",
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
-    "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count",
+    "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision",
 )
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -162,6 +162,8 @@ def load_library() -> C.CDLL:
     lib.hmp_debug_fis.argtypes = [C.c_void_p, C.c_void_p, _i, C.c_void_p]
     lib.hmp_debug_last_forces.argtypes = [C.c_void_p, _i, C.c_void_p]
     lib.hmp_num_steps.argtypes = [C.c_void_p]
+    lib.hmp_set_precision.argtypes = [C.c_void_p, _i]
+    lib.hmp_set_precision.restype = C.c_int
     lib.hmp_launch_count.restype = C.c_int64
     lib.hmp_launch_count.argtypes = [C.c_void_p]
     for name in ("hmp_set_params", "hmp_set_costmap", "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan",
@@ -227,6 +229,9 @@ class Planner:
     # ---- configuration -------------------------------------------------------------------------
     def set_params(self, params: HmpParams):
         self._check(self._lib.hmp_set_params(self._ctx, C.byref(params)))
+
+    def set_precision(self, fp64: bool):
+        self._check(self._lib.hmp_set_precision(self._ctx, 1 if fp64 else 0))
 
     def set_costmap(self, cells: np.ndarray, origin_x: float, origin_y: float, resolution: float):
         cells = np.ascontiguousarray(cells, dtype=np.uint8)

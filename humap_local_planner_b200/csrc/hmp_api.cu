@@ -22,18 +22,18 @@
 
 static_assert(sizeof(DevParams) % 16 == 0, "DevParams is copied with cp.async.bulk (16-byte granules)");
 static_assert(sizeof(DevScene) % 16 == 0, "DevScene header must keep the arrays 16-byte aligned");
-static_assert(sizeof(DevDynamic) == 32 && sizeof(DevPerson) == 64 && sizeof(DevGroup) == 32 && sizeof(DevStatic) == 8,
+static_assert(sizeof(DevDynamic) == 64 && sizeof(DevPerson) == 64 && sizeof(DevGroup) == 32 && sizeof(DevStatic) == 16,
               "device record sizes are relied upon by the float4 loads in the kernel");
 
 extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_stride, int costmap_in_smem);
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
-extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int* blocks_per_sm);
+extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
                                                      double* cost, cudaStream_t stream);
-extern "C" cudaError_t hmp_dev_launch_fis(const float* in4, int n, float* out2, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
 
 namespace {
 
@@ -136,6 +136,7 @@ struct HmpContext {
 	double hv_prev[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	std::vector<double> footprint;
 	bool have_footprint = false;
+	int precise = 0;
 
 	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
 	HostBuf h_stage, h_out;
@@ -178,50 +179,53 @@ int build_dev_params(const HmpContext* ctx, const HmpSampling* sampling, int n_e
 		D.n_ttc_extra = n;
 	}
 	const HmpLimits& L = P.limits;
-	D.max_vel_x = (float)L.max_vel_x;
-	D.min_vel_x = (float)L.min_vel_x;
-	D.max_vel_y = (float)L.max_vel_y;
-	D.min_vel_y = (float)L.min_vel_y;
-	D.max_vel_theta = (float)L.max_vel_theta;
-	D.min_vel_theta = (float)L.min_vel_theta;
-	D.max_vel_trans = (float)L.max_vel_trans;
-	D.min_vel_trans = (float)L.min_vel_trans;
-	D.acc_x = (float)L.acc_lim_x;
-	D.acc_y = (float)L.acc_lim_y;
-	D.acc_th = (float)L.acc_lim_theta;
-	D.acc_decel = (float)std::hypot(L.acc_lim_x, L.acc_lim_y);
-	D.rot_comp = (float)L.twist_rotation_compensation;
-	D.back_max = (float)((L.min_vel_x < 0.0) ? std::fabs(L.min_vel_x) : 0.0);
+	D.max_vel_x = L.max_vel_x;
+	D.min_vel_x = L.min_vel_x;
+	D.max_vel_y = L.max_vel_y;
+	D.min_vel_y = L.min_vel_y;
+	D.max_vel_theta = L.max_vel_theta;
+	D.min_vel_theta = L.min_vel_theta;
+	D.max_vel_trans = L.max_vel_trans;
+	D.min_vel_trans = L.min_vel_trans;
+	D.acc_x = L.acc_lim_x;
+	D.acc_y = L.acc_lim_y;
+	D.acc_th = L.acc_lim_theta;
+	D.acc_decel = std::hypot(L.acc_lim_x, L.acc_lim_y);
+	D.rot_comp = L.twist_rotation_compensation;
+	D.back_max = (L.min_vel_x < 0.0) ? std::fabs(L.min_vel_x) : 0.0;
 	D.maintain_rate = L.maintain_vel_components_rate != 0;
 
 	const HmpSfm& S = P.sfm;
 	D.fov_method = S.fov_factor_method;
 	D.filter_forces = S.filter_forces != 0;
 	D.disable_interaction = S.disable_interaction_forces != 0;
-	D.mass = (float)S.mass;
-	D.m_over_tau = (float)(S.mass * (1 / (double)(float)S.relaxation_time));
-	D.k_int = (float)S.internal_force_factor;
-	D.k_stat = (float)S.static_interaction_force_factor;
-	D.k_dyn = (float)S.dynamic_interaction_force_factor;
-	D.min_force = (float)S.min_force;
-	D.max_force = (float)S.max_force;
+	D.mass = S.mass;
+	D.m_over_tau = S.mass * (1 / (double)(float)S.relaxation_time);
+	D.k_int = S.internal_force_factor;
+	D.k_stat = S.static_interaction_force_factor;
+	D.k_dyn = S.dynamic_interaction_force_factor;
+	D.min_force = S.min_force;
+	D.max_force = S.max_force;
 	// computeFactorFOV(angle, 2 * cfg.fov, gaussian): half angle cfg.fov, variance cfg.fov^2, PDF not normalised to 1
-	D.fov_half = (float)S.fov;
-	D.fov_gauss_scale = (float)(1.0 / (std::sqrt(S.fov * S.fov) * std::sqrt(2.0 * PI)));
-	D.fov_neg_inv_2var = (float)(-1.0 / (2.0 * S.fov * S.fov));
+	D.fov_half_d = S.fov;
+	D.fov_gauss_scale_d = 1.0 / (std::sqrt(S.fov * S.fov) * std::sqrt(2.0 * PI));
+	D.fov_neg_inv_2var_d = -1.0 / (2.0 * S.fov * S.fov);
+	D.fov_half = (float)D.fov_half_d;
+	D.fov_gauss_scale = (float)D.fov_gauss_scale_d;
+	D.fov_neg_inv_2var = (float)D.fov_neg_inv_2var_d;
 	const double base[9] = {S.speed_desired, S.an, S.bn, S.cn, S.ap, S.bp, S.cp, S.aw, S.bw};
 	for (int i = 0; i < 9; ++i) D.base[i] = (float)base[i];
 
 	const HmpFis& F = P.fis;
 	D.fis_on = (!D.disable_interaction && !(F.force_factor <= 0.0)) ? 1 : 0;
 	D.fis_fov_method = F.fov_factor_method;
-	D.fis_force_factor = (float)F.force_factor;
-	D.fis_range = (float)F.human_action_range;
-	D.fis_fov_half = (float)(F.fov / 2.0);
+	D.fis_force_factor_d = F.force_factor;
+	D.fis_range_d = F.human_action_range;
+	D.fis_fov_half_d = F.fov / 2.0;
 	{
 		double var = (F.fov / 2.0) * (F.fov / 2.0);
-		D.fis_gauss_scale = (float)(1.0 / (std::sqrt(var) * std::sqrt(2.0 * PI)));
-		D.fis_neg_inv_2var = (float)(-1.0 / (2.0 * var));
+		D.fis_gauss_scale_d = 1.0 / (std::sqrt(var) * std::sqrt(2.0 * PI));
+		D.fis_neg_inv_2var_d = -1.0 / (2.0 * var);
 	}
 
 	// amplifier lists
@@ -310,7 +314,7 @@ int build_dev_params(const HmpContext* ctx, const HmpSampling* sampling, int n_e
 size_t scene_blob_bytes(const HmpWorld& w) {
 	// worst case: every obstacle appears in both the dynamic and the static array (App. A #5)
 	size_t b = sizeof(DevScene);
-	b += ((size_t)w.n_obstacles * sizeof(DevStatic) + 15) / 16 * 16;
+	b += (size_t)w.n_obstacles * sizeof(DevStatic);
 	b += (size_t)w.n_obstacles * sizeof(DevDynamic);
 	b += (size_t)w.n_people * sizeof(DevPerson);
 	b += (size_t)w.n_groups * sizeof(DevGroup);
@@ -327,9 +331,16 @@ void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev,
 	H.yaw0 = wrap(w.robot_yaw);
 	// computeVelocityGlobal(vel_, pose_), humap_planner.cpp:366-369
 	double cy = std::cos(H.yaw0), sy = std::sin(H.yaw0);
-	H.u0x = (float)(w.vel_x * cy - w.vel_y * sy);
-	H.u0y = (float)(w.vel_x * sy + w.vel_y * cy);
-	H.u0w = (float)w.vel_th;
+	H.u0x_d = w.vel_x * cy - w.vel_y * sy;
+	H.u0y_d = w.vel_x * sy + w.vel_y * cy;
+	H.u0w_d = w.vel_th;
+	H.u0x = (float)H.u0x_d;
+	H.u0y = (float)H.u0y_d;
+	H.u0w = (float)H.u0w_d;
+	H.glx_d = w.goal_local_x - w.robot_x;
+	H.gly_d = w.goal_local_y - w.robot_y;
+	H.gx_d = w.goal_x - w.robot_x;
+	H.gy_d = w.goal_y - w.robot_y;
 	H.vlx = (float)w.vel_x;
 	H.vly = (float)w.vel_y;
 	H.vlw = (float)w.vel_th;
@@ -348,24 +359,24 @@ void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev,
 		bool dyn0 = (o.force_dynamic != 0) || moving;                        // world.cpp:49
 		double d0x = o.obj_x - o.robot_x, d0y = o.obj_y - o.robot_y;
 		if (!dyn0) {
-			st_always.push_back({(float)d0x, (float)d0y});
+			st_always.push_back({d0x, d0y});
 			continue;
 		}
 		DevDynamic d;
-		d.d0x = (float)d0x;
-		d.d0y = (float)d0y;
-		d.vx = (float)o.vx;
-		d.vy = (float)o.vy;
-		d.psi0 = (float)wrap(o.robot_yaw);
-		d.dir_beta = (float)wrap(std::atan2(o.vy, o.vx));
-		d.speed = (float)std::hypot(o.vx, o.vy);
-		d._pad = 0.f;
+		d.d0x = d0x;
+		d.d0y = d0y;
+		d.vx = o.vx;
+		d.vy = o.vy;
+		d.psi0 = wrap(o.robot_yaw);
+		d.dir_beta = wrap(std::atan2(o.vy, o.vx));
+		d.speed = std::hypot(o.vx, o.vy);
+		d._pad = 0.0;
 		if (moving) {
 			dy_always.push_back(d);
 		} else {
 			// dynamic at step 0 only: advanced once by v dt in the first World::predict, then static (world.cpp:101-110)
 			dy_first.push_back(d);
-			st_later.push_back({(float)(d0x + o.vx * dt), (float)(d0y + o.vy * dt)});
+			st_later.push_back({d0x + o.vx * dt, d0y + o.vy * dt});
 		}
 	}
 	H.n_static0 = (int)st_always.size();
@@ -376,7 +387,7 @@ void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev,
 	H.n_groups = w.n_groups;
 	uint32_t off = sizeof(DevScene);
 	H.off_static = off;
-	off += (uint32_t)(((size_t)H.n_static * sizeof(DevStatic) + 15) / 16 * 16);
+	off += (uint32_t)((size_t)H.n_static * sizeof(DevStatic));
 	H.off_dynamic = off;
 	off += (uint32_t)((size_t)H.n_dynamic * sizeof(DevDynamic));
 	H.off_people = off;
@@ -493,7 +504,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		}
 	}
 	int bps = 0;
-	CU(hmp_dev_occupancy(smem, &bps));
+	CU(hmp_dev_occupancy(smem, ctx->precise, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
 		return HMP_E_CUDA;
@@ -726,6 +737,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
 	A.costmap_stride = ctx->costmap_stride;
 	A.costmap_in_smem = in_smem;
+	A.precise = ctx->precise;
 	A.mapgrids = (const float*)ctx->d_mapgrids.p;
 	A.n_work = C;
 	A.totals = (double*)ctx->d_totals.p;
@@ -1012,6 +1024,7 @@ int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n, do
 	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
 	A.costmap_stride = ctx->costmap_stride;
 	A.costmap_in_smem = in_smem;
+	A.precise = ctx->precise;
 	A.mapgrids = (const float*)ctx->d_mapgrids.p;
 	A.cand_list = d_idx;
 	A.n_work = n;
@@ -1130,18 +1143,28 @@ int hmp_debug_fis(HmpContext* ctx, const double* in4, int32_t n, double* out2) {
 	}
 	CU(cudaSetDevice(ctx->device));
 	int rc;
-	if ((rc = ctx->d_dbg.ensure((size_t)n * 6 * sizeof(float)))) return rc;
-	std::vector<float> hin((size_t)n * 4), hout((size_t)n * 2);
-	for (size_t i = 0; i < hin.size(); ++i) hin[i] = (float)in4[i];
-	float* din = (float*)ctx->d_dbg.p;
-	float* dout = din + (size_t)n * 4;
+	if ((rc = ctx->d_dbg.ensure((size_t)n * 6 * sizeof(double)))) return rc;
+	double* din = (double*)ctx->d_dbg.p;
+	double* dout = din + (size_t)n * 4;
 	cudaStream_t st = ctx->stream;
-	CU(cudaMemcpyAsync(din, hin.data(), hin.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-	CU(hmp_dev_launch_fis(din, n, dout, st));
+	CU(cudaMemcpyAsync(din, in4, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_fis(din, n, dout, ctx->precise, st));
 	ctx->launches++;
-	CU(cudaMemcpyAsync(hout.data(), dout, hout.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(out2, dout, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	for (size_t i = 0; i < hout.size(); ++i) out2[i] = hout[i];
+	return HMP_OK;
+}
+
+// 0 (default): FP32 object loops and FIS -- the fast path the benchmarks time. 1: the same kernel instantiated
+// with FP64 object loops and FIS (vertex quantisation included) -- parity mode used to separate restatement
+// errors from FP32 rounding.
+int hmp_set_precision(HmpContext* ctx, int32_t fp64) {
+	if (!ctx) {
+		set_err("null context");
+		return HMP_E_INVALID;
+	}
+	ctx->precise = fp64 ? 1 : 0;
+	ctx->last_valid = false;
 	return HMP_OK;
 }
 

@@ -23,17 +23,19 @@
  * rollout dist_v = d0 - (c - c0) because World::predict only translates the robot-side point with the
  * centroid (world.cpp:107-110). */
 struct DevStatic {
-	float d0x, d0y;
+	double d0x, d0y;
 };
 
-/* One object treated with the DYNAMIC formulation (DynamicObject, world.h:43-59). */
+/* One object treated with the DYNAMIC formulation (DynamicObject, world.h:43-59). Geometry is FP64: the
+ * dynamic interaction force can reach 1e4..1e6 N for amplified parameter sets and the twist amplifies any
+ * rounding of its direction by |F| / m per step. */
 struct DevDynamic {
-	float d0x, d0y;   /* object point - robot-side point at t = 0                     */
-	float vx, vy;     /* object velocity (global)                                     */
-	float psi0;       /* yaw of the robot-side closest-point pose at t = 0            */
-	float dir_beta;   /* wrap(direction(vel)), world.cpp:183                          */
-	float speed;      /* |vel_xy|, world.cpp:180-181                                  */
-	float _pad;
+	double d0x, d0y;  /* object point - robot-side point at t = 0                     */
+	double vx, vy;    /* object velocity (global)                                     */
+	double psi0;      /* yaw of the robot-side closest-point pose at t = 0            */
+	double dir_beta;  /* wrap(direction(vel)), world.cpp:183                          */
+	double speed;     /* |vel_xy|, world.cpp:180-181                                  */
+	double _pad;
 };
 
 /* humap_local_planner::Person prediction source (person.h, trajectory.h:160-193) + covariances +
@@ -57,6 +59,8 @@ struct DevGroup {
 /* Per-scene header. Arrays follow in one blob; offsets are in bytes from the blob start. */
 struct alignas(16) DevScene {
 	double x0, y0, yaw0;          /* robot pose at t = 0 (absolute, map frame)                         */
+	double u0x_d, u0y_d, u0w_d;   /* robot global velocity at t = 0 (computeVelocityGlobal(vel_, pose_)) */
+	double glx_d, gly_d, gx_d, gy_d;  /* goal_local_ and goal_ relative to (x0, y0)                     */
 	float u0x, u0y, u0w;          /* robot global velocity at t = 0 (computeVelocityGlobal(vel_, pose_)) */
 	float vlx, vly, vlw;          /* vel_: current base-frame velocity (smoothness critics)            */
 	float glx, gly;               /* goal_local_ - (x0, y0)                                            */
@@ -82,26 +86,28 @@ struct alignas(16) DevParams {
 	double ttc_rollout_time_d;
 	float dt;
 	float people_dt;
-	/* --- limits */
-	float max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_vel_theta, min_vel_theta;
-	float max_vel_trans, min_vel_trans;
-	float acc_x, acc_y, acc_th, acc_decel;     /* acc_decel = hypot(acc_x, acc_y)  */
-	float rot_comp;
-	float back_max;               /* (min_vel_x < 0) ? |min_vel_x| : 0              */
-	int32_t maintain_rate;
+	/* --- limits (FP64: the twist / limit arithmetic of every step is done in double) */
+	double max_vel_x, min_vel_x, max_vel_y, min_vel_y, max_vel_theta, min_vel_theta;
+	double max_vel_trans, min_vel_trans;
+	double acc_x, acc_y, acc_th, acc_decel;     /* acc_decel = hypot(acc_x, acc_y)  */
+	double rot_comp;
+	double back_max;               /* (min_vel_x < 0) ? |min_vel_x| : 0              */
 	/* --- SFM */
+	double mass, m_over_tau;
+	double k_int, k_stat, k_dyn, min_force, max_force;
+	double fov_half_d;             /* linear method: half angle = cfg.fov                */
+	double fov_gauss_scale_d;      /* 1 / (sigma sqrt(2 pi)), sigma = cfg.fov            */
+	double fov_neg_inv_2var_d;     /* -1 / (2 sigma^2)                                   */
+	float fov_half, fov_gauss_scale, fov_neg_inv_2var;   /* FP32 copies for the static-object loop */
+	int32_t maintain_rate;
 	int32_t fov_method, filter_forces, disable_interaction;
-	float mass, m_over_tau;
-	float k_int, k_stat, k_dyn, min_force, max_force;
-	float fov_half;               /* linear method: half angle = cfg.fov                */
-	float fov_gauss_scale;        /* 1 / (sigma sqrt(2 pi)), sigma = cfg.fov            */
-	float fov_neg_inv_2var;       /* -1 / (2 sigma^2)                                   */
+	int32_t _pads;
 	float base[9];                /* (float)cfg.{speed_desired, an, bn, cn, ap, bp, cp, aw, bw}: SFM float members */
 	/* --- FIS */
 	int32_t fis_on, fis_fov_method;
-	float fis_force_factor, fis_range;
-	float fis_fov_half;           /* linear method: cfg.fov / 2                        */
-	float fis_gauss_scale, fis_neg_inv_2var;
+	double fis_force_factor_d, fis_range_d;
+	double fis_fov_half_d;        /* linear method: cfg.fov / 2                        */
+	double fis_gauss_scale_d, fis_neg_inv_2var_d;
 	/* --- candidates */
 	int32_t amp_n[HMP_NUM_AMPLIFIERS];
 	int32_t n_grid;               /* product of amp_n                                  */
@@ -141,6 +147,8 @@ struct KernelArgs {
 	const uint8_t* costmaps;         /* n_scenes costmaps, stride costmap_stride bytes (mult of 16) */
 	uint32_t costmap_stride;
 	int32_t costmap_in_smem;
+	int32_t precise;                 /* 1: object loops and the FIS in FP64 (parity mode), 0: FP32 (fast mode) */
+	int32_t _padk;
 	const float* mapgrids;           /* [n_scenes][4][size_y * size_x]                            */
 	/* selection */
 	const int32_t* cand_list;        /* explicit candidate indices (detail mode) or null          */

@@ -269,6 +269,11 @@ int hmp_abi_version(void);
  *      setXShift calls of updateLocalCosts (:1054-1141) ----------------------------------------- */
 int hmp_set_params(HmpContext* ctx, const HmpParams* params);
 
+/* Arithmetic of the per-object loops (static / dynamic interaction forces, fuzzy inference): 0 = FP32 (default,
+ * the fast path), 1 = FP64 (parity mode: isolates restatement errors from FP32 rounding; several times slower).
+ * Pose integration, twist / limit arithmetic, cell indexing and the weighted total are FP64 in both modes. */
+int hmp_set_precision(HmpContext* ctx, int32_t fp64);
+
 /* Replaces the costmap_2d::Costmap2D* every critic holds (row-major, index = my * size_x + mx). */
 int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y,
                     double origin_x, double origin_y, double resolution);

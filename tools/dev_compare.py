@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--fis", type=int, default=1)
     ap.add_argument("--forces", type=int, default=-1)
     ap.add_argument("--worst", type=int, default=0)
+    ap.add_argument("--precise", type=int, default=0)
     a = ap.parse_args()
     cfg = scenes.CONFIGS[a.cfg]
     sc = scenes.make_scene(cfg, a.seed)
@@ -29,6 +30,7 @@ def main():
     smp = scenes.make_sampling(cfg)
     pl = Planner(0)
     pl.set_params(params)
+    pl.set_precision(bool(a.precise))
     pl.set_scene(sc)
     t = time.time()
     res, poses = pl.plan(sc.world, smp)
