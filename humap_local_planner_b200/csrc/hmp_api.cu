@@ -513,6 +513,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	long long resident = (long long)ctx->sm_count * bps;
 	long long need = ((long long)C + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK;
 	long long per_scene = std::max<long long>(1, std::min<long long>(need, (resident + pl.n_scenes - 1) / pl.n_scenes));
+	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes\n", smem, bps, per_scene, pl.n_scenes);
 	*blocks_x_out = (int)per_scene;
 	*smem_out = smem;
 	*costmap_in_smem_out = in_smem;

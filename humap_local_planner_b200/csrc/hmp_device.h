@@ -17,6 +17,9 @@
 #define HMP_DEV_MAX_KERNEL_PTS 9   /* centre + 8 offsets (RECTANGLE kernel) */
 #define HMP_WARPS_PER_BLOCK 8
 #define HMP_THREADS_PER_BLOCK (32 * HMP_WARPS_PER_BLOCK)
+#ifndef HMP_MIN_BLOCKS
+#define HMP_MIN_BLOCKS 2
+#endif
 
 /* Rollout-invariant record of one object treated with the STATIC interaction formulation
  * (reference StaticObject, world.h:24-41). d0 = object point - robot-side point at t = 0; during the
