@@ -118,7 +118,7 @@ ABI_SYMBOLS = (
     "hmp_create", "hmp_destroy", "hmp_last_error", "hmp_abi_version", "hmp_set_params", "hmp_set_costmap",
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
-    "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision",
+    "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
 )
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -163,6 +163,10 @@ def load_library() -> C.CDLL:
     lib.hmp_debug_last_forces.argtypes = [C.c_void_p, _i, C.c_void_p]
     lib.hmp_num_steps.argtypes = [C.c_void_p]
     lib.hmp_set_precision.argtypes = [C.c_void_p, _i]
+    lib.hmp_compute_mapgrid.argtypes = [C.c_void_p, _i, C.c_void_p, _i, _i, _d]
+    lib.hmp_compute_mapgrid.restype = C.c_int
+    lib.hmp_get_mapgrid.argtypes = [C.c_void_p, _i, C.c_void_p]
+    lib.hmp_get_mapgrid.restype = C.c_int
     lib.hmp_set_precision.restype = C.c_int
     lib.hmp_launch_count.restype = C.c_int64
     lib.hmp_launch_count.argtypes = [C.c_void_p]
@@ -241,6 +245,15 @@ class Planner:
     def set_mapgrid(self, grid: int, target_dist: np.ndarray, hv_prev: float = 0.0):
         t = np.ascontiguousarray(target_dist, dtype=np.float64)
         self._check(self._lib.hmp_set_mapgrid(self._ctx, grid, _ptr(t), float(hv_prev)))
+
+    def compute_mapgrid(self, grid: int, plan_xy: np.ndarray, local_goal: bool, hv_prev: float = 0.0):
+        p = np.ascontiguousarray(plan_xy, dtype=np.float64).reshape(-1, 2)
+        self._check(self._lib.hmp_compute_mapgrid(self._ctx, grid, _ptr(p), p.shape[0], 1 if local_goal else 0, float(hv_prev)))
+
+    def get_mapgrid(self, grid: int, shape) -> np.ndarray:
+        out = np.zeros(shape, dtype=np.float64)
+        self._check(self._lib.hmp_get_mapgrid(self._ctx, grid, _ptr(out)))
+        return out
 
     def set_footprint(self, xy: np.ndarray):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)

@@ -33,6 +33,8 @@ extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const dou
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
                                                      double* cost, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_wavefront(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
+                                                cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
 
 namespace {
@@ -135,10 +137,11 @@ struct HmpContext {
 	bool have_grid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	double hv_prev[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	std::vector<double> footprint;
+	std::vector<uint8_t> h_cells;   // host copy of the single-scene costmap (seed test of the device wave front)
 	bool have_footprint = false;
 	int precise = 0;
 
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
+	DevBuf d_seeds, d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -575,7 +578,7 @@ void hmp_destroy(HmpContext* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
+	DevBuf* bufs[] = {&ctx->d_seeds, &ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
 	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
@@ -625,6 +628,7 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
 	rc = ctx->h_stage.ensure(std::max<size_t>(stride, cells_n * sizeof(float)));
 	if (rc) return rc;
 	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->h_cells.assign(cells, cells + cells_n);
 	std::memcpy(ctx->h_stage.p, cells, cells_n);
 	std::memset((unsigned char*)ctx->h_stage.p + cells_n, 0, stride - cells_n);
 	CU(cudaMemcpyAsync(ctx->d_costmaps.p, ctx->h_stage.p, stride, cudaMemcpyHostToDevice, ctx->stream));
@@ -669,6 +673,103 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 	ctx->have_grid[grid] = true;
 	ctx->hv_prev[grid] = highest_valid_cost_prev;
 	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+// Host part of base_local_planner::MapGrid::setTargetCells / setLocalGoal [RECALLED, SURVEY App. B]: densify the plan
+// to the costmap resolution (adjustPlanResolution) and collect the seed cells; the wave front itself runs on the device.
+int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, int32_t n_plan, int32_t local_goal,
+                        double highest_valid_cost_prev) {
+	if (!ctx || grid < 0 || grid >= HMP_NUM_MAPGRIDS || n_plan < 0 || (n_plan > 0 && !plan_xy)) {
+		set_err("bad mapgrid arguments");
+		return HMP_E_INVALID;
+	}
+	if (!ctx->have_costmap) {
+		set_err("hmp_set_costmap must precede hmp_compute_mapgrid");
+		return HMP_E_NOT_READY;
+	}
+	CU(cudaSetDevice(ctx->device));
+	const int sx = ctx->size_x, sy = ctx->size_y;
+	const size_t n = (size_t)sx * sy;
+	if ((n + 31) / 32 * 4 > 200 * 1024) {
+		set_err("costmap too large for the on-device wave front");
+		return HMP_E_CAPACITY;
+	}
+	auto world_to_map = [&](double wx, double wy, int& mx, int& my) {
+		if (wx < ctx->origin_x || wy < ctx->origin_y) return false;
+		mx = (int)((wx - ctx->origin_x) / ctx->resolution);
+		my = (int)((wy - ctx->origin_y) / ctx->resolution);
+		return mx < sx && my < sy;
+	};
+	// the costmap cells are needed for the NO_INFORMATION test of the seeds: keep a host copy from hmp_set_costmap
+	if (ctx->h_cells.size() != n) {
+		set_err("host copy of the costmap is missing");
+		return HMP_E_NOT_READY;
+	}
+	std::vector<int> seeds;
+	if (n_plan > 0) {
+		std::vector<double> px, py;
+		double last_x = plan_xy[0], last_y = plan_xy[1];
+		px.push_back(last_x);
+		py.push_back(last_y);
+		const double min_sq = ctx->resolution * ctx->resolution;
+		for (int i = 1; i < n_plan; ++i) {
+			double lx = plan_xy[2 * i], ly = plan_xy[2 * i + 1];
+			double sq = (lx - last_x) * (lx - last_x) + (ly - last_y) * (ly - last_y);
+			if (sq > min_sq) {
+				int steps = (int)std::ceil(std::sqrt(sq) / ctx->resolution);
+				double dx = (lx - last_x) / steps, dy = (ly - last_y) / steps;
+				for (int j = 1; j < steps; ++j) {
+					px.push_back(last_x + j * dx);
+					py.push_back(last_y + j * dy);
+				}
+			}
+			px.push_back(lx);
+			py.push_back(ly);
+			last_x = lx;
+			last_y = ly;
+		}
+		bool started = false;
+		int goal = -1;
+		for (size_t i = 0; i < px.size(); ++i) {
+			int mx, my;
+			if (world_to_map(px[i], py[i], mx, my) && ctx->h_cells[(size_t)my * sx + mx] != 255) {
+				if (local_goal) goal = my * sx + mx;
+				else seeds.push_back(my * sx + mx);
+				started = true;
+			} else if (started) {
+				break;
+			}
+		}
+		if (local_goal && goal >= 0) seeds.push_back(goal);
+	}
+	int rc = ctx->d_seeds.ensure(std::max<size_t>(1, seeds.size()) * sizeof(int));
+	if (rc) return rc;
+	cudaStream_t st = ctx->stream;
+	CU(cudaStreamSynchronize(st));
+	if (!seeds.empty()) CU(cudaMemcpyAsync(ctx->d_seeds.p, seeds.data(), seeds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p, sx, sy, (const int*)ctx->d_seeds.p, (int)seeds.size(),
+	                            (float*)ctx->d_mapgrids.p + (size_t)grid * n, st));
+	ctx->launches++;
+	CU(cudaStreamSynchronize(st));   // `seeds` is a stack-owned staging buffer
+	ctx->have_grid[grid] = true;
+	ctx->hv_prev[grid] = highest_valid_cost_prev;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_get_mapgrid(HmpContext* ctx, int32_t grid, double* target_dist_out) {
+	if (!ctx || grid < 0 || grid >= HMP_NUM_MAPGRIDS || !target_dist_out || !ctx->have_grid[grid]) {
+		set_err("bad arguments or grid not set");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)ctx->size_x * ctx->size_y;
+	std::vector<float> tmp(n);
+	CU(cudaMemcpyAsync(tmp.data(), (const float*)ctx->d_mapgrids.p + (size_t)grid * n, n * sizeof(float), cudaMemcpyDeviceToHost,
+	                   ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (size_t i = 0; i < n; ++i) target_dist_out[i] = tmp[i];
 	return HMP_OK;
 }
 

@@ -269,7 +269,10 @@ def make_scene(cfg: CycleConfig, seed: int, robot_xy=(0.0, 0.0), robot_yaw: floa
     w.obstacles, w.people, w.groups = obs_arr, ppl_arr, grp_arr
     w.n_obstacles, w.n_people, w.n_groups = len(obstacles), len(people), len(groups)
     hv_prev = (80.0, 80.0, 80.0, 80.0)
-    return Scene(w, obs_arr, ppl_arr, grp_arr, cells, origin_x, origin_y, res, grids, circular_footprint(), hv_prev)
+    sc = Scene(w, obs_arr, ppl_arr, grp_arr, cells, origin_x, origin_y, res, grids, circular_footprint(), hv_prev)
+    # the target poses each MapGridCostFunction received (setTargetPoses) and its is_local_goal_function_ flag
+    sc.plans = [(plan, False), (plan, True), (plan, False), (front_plan, True)]
+    return sc
 
 
 def make_params(cfg: CycleConfig, fis: bool = True):

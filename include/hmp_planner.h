@@ -284,6 +284,15 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
  * unreachableCellCosts()), which is checked. */
 int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, double highest_valid_cost_prev);
 
+/* Replaces MapGridCostFunction::setTargetPoses + prepare() (map_grid_cost_function.cpp:63-79 ->
+ * base_local_planner::MapGrid::setTargetCells / setLocalGoal + computeTargetDistance): computes the wave-front grid of
+ * slot `grid` ON THE DEVICE from the plan poses (xy interleaved, map frame) and the costmap set by hmp_set_costmap, so
+ * that neither the host wave front nor the 4-byte-per-cell upload is needed. local_goal = is_local_goal_function_. */
+int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, int32_t n_plan, int32_t local_goal,
+                        double highest_valid_cost_prev);
+/* Reads a MapGrid slot back (row-major doubles); diagnostics / parity tests. */
+int hmp_get_mapgrid(HmpContext* ctx, int32_t grid, double* target_dist_out);
+
 /* Replaces ObstacleSeparationCostFunction::setFootprint (humap_planner.cpp:1059); xy interleaved. */
 int hmp_set_footprint(HmpContext* ctx, const double* xy, int32_t n_points);
 

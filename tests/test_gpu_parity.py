@@ -460,3 +460,77 @@ def test_batched_scenes_equal_single_cycles(planner):
         assert res[s].best_index == singles[s][0] and res[s].best_total == singles[s][1]
         assert res[s].n_valid == singles[s][2]
         assert np.array_equal(tot[s], singles[s][3])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row 1: MapGrid wave front on the device, bit-exact against the oracle's queue-based BFS
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,seed", [("cfg0", 0), ("cfg0", 1), ("cfg2", 2), ("cfg2", 3)])
+def test_device_wavefront_bit_exact(planner, name, seed):
+    cfg, sc, params, smp = _setup(planner, name, seed)
+    L = ob.lib()
+    L.orc_mapgrid_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p]
+    L.orc_mapgrid_compute.restype = None
+    rng = np.random.default_rng(seed)
+    wiggly = np.stack([np.linspace(-1.0, 6.5, 40), 0.8 * np.sin(np.linspace(0, 5, 40)) + rng.uniform(-0.05, 0.05, 40)], axis=1)
+    plans = list(sc.plans) + [(wiggly, False), (wiggly, True), (np.zeros((0, 2)), False), (np.array([[50.0, 50.0]]), True)]
+    for k, (plan, local_goal) in enumerate(plans):
+        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        planner.compute_mapgrid(k % 4, plan, local_goal, 0.0)
+        got = planner.get_mapgrid(k % 4, sc.cells.shape)
+        ref = np.zeros_like(got)
+        L.orc_mapgrid_compute(sc.cells.ctypes.data, sc.size_x, sc.size_y, sc.origin_x, sc.origin_y, sc.resolution,
+                              plan.ctypes.data, plan.shape[0], 1 if local_goal else 0, ref.ctypes.data)
+        assert np.array_equal(got, ref), (k, int((got != ref).sum()))
+
+
+def test_cycle_with_device_wavefront_equals_uploaded_grids(planner):
+    cfg, sc, params, smp = _setup(planner, "cfg1", 3)
+    r1, p1 = planner.plan(sc.world, smp)
+    t1 = planner.explored_totals(r1.n_candidates)
+    for g, (plan, local_goal) in enumerate(sc.plans):
+        planner.compute_mapgrid(g, plan, local_goal, sc.hv_prev[g])
+    r2, p2 = planner.plan(sc.world, smp)
+    assert r2.best_index == r1.best_index and r2.best_total == r1.best_total
+    assert np.array_equal(planner.explored_totals(r2.n_candidates), t1) and np.array_equal(p1, p2)
+
+
+def test_batch_64_scenes(planner):
+    """A slice of BASELINE config 4 (batched independent scenes, 4k candidates each): every scene's argmin equals the
+    argmin of its explored totals, and sampled scenes equal their single-scene cycle."""
+    cfg = scenes.CONFIGS["cfg3"]
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    envs = [scenes.make_scene(cfg, 300 + e) for e in range(8)]
+    n = 64
+    # 8 environments x 8 robot states each: independent worlds for the kernel (own blob, own costmap / grids copy)
+    worlds, cells, grids = [], [], [[] for _ in range(4)]
+    keep = []
+    for s in range(n):
+        e = envs[s % 8]
+        sc = scenes.make_scene(cfg, 300 + s % 8, base_vel=(0.1 + 0.15 * (s // 8), 0.0, 0.05 * ((s // 8) - 3)))
+        keep.append(sc)
+        worlds.append(sc.world)
+        cells.append(sc.cells)
+        for g in range(4):
+            grids[g].append(sc.grids[g])
+    planner.set_params(params)
+    planner.set_scene(keep[0])
+    hv = np.array([sc.hv_prev for sc in keep])
+    res = planner.plan_batch(worlds, np.stack(cells), [np.stack(g) for g in grids], smp, hv_prev=hv)
+    Cn = res[0].n_candidates
+    assert Cn == 4096
+    tot = planner.explored_totals(n * Cn).reshape(n, Cn)
+    for s in range(n):
+        valid = np.where(tot[s] >= 0)[0]
+        if len(valid) == 0:
+            assert res[s].best_index == -1
+            continue
+        b = valid[np.argmin(tot[s][valid])]
+        assert res[s].best_index == b and res[s].best_total == tot[s][b] and res[s].n_valid == len(valid)
+    for s in (0, 17, 63):
+        planner.set_params(params)
+        planner.set_scene(keep[s])
+        r, _ = planner.plan(keep[s].world, smp, want_poses=False)
+        assert r.best_index == res[s].best_index and r.best_total == res[s].best_total
