@@ -247,6 +247,22 @@ def main():
         r, poses = full_cycle()
         e2e_times.append(time.perf_counter() - t0)
     barrier()
+    # variant: MapGridCostFunction::prepare() replaced as well (wave fronts computed on the device from the plan poses)
+    def full_cycle_device_grids():
+        pl.set_costmap(scene.cells, scene.origin_x, scene.origin_y, scene.resolution)
+        for g, (plan, local_goal) in enumerate(scene.plans):
+            pl.compute_mapgrid(g, plan, local_goal, scene.hv_prev[g])
+        pl.set_footprint(scene.footprint)
+        return pl.plan(scene.world, sampling, want_poses=True)
+    full_cycle_device_grids()
+    e2e_dev_times = []
+    for _ in range(min(args.steps, 10)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r_dev, _ = full_cycle_device_grids()
+        e2e_dev_times.append(time.perf_counter() - t0)
+    assert r_dev.best_index == r.best_index and r_dev.best_total == r.best_total, "device wave front changed the selection"
+    barrier()
     t_e2e = torch.tensor([sum(e2e_times)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -281,6 +297,7 @@ def main():
                        "l2": "flushed with a 256 MiB write between timed iterations", "timing": "CUDA events on the launching stream"},
             "p50_cycle_ms": statistics.median(dev_ms), "p99_cycle_ms": sorted(dev_ms)[min(len(dev_ms) - 1, int(0.99 * len(dev_ms)))],
             "p50_cycle_ms_e2e": 1e3 * statistics.median(e2e_times),
+            "p50_cycle_ms_e2e_device_mapgrids": 1e3 * statistics.median(e2e_dev_times),
             "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
             "e2e": {"value": world * C * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),

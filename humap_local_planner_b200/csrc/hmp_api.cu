@@ -35,6 +35,8 @@ extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const u
                                                      double* cost, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_wavefront(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
                                                 cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_wavefront_queue(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
+                                                      int* status, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
 
 namespace {
@@ -141,7 +143,13 @@ struct HmpContext {
 	bool have_footprint = false;
 	int precise = 0;
 
-	DevBuf d_seeds, d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
+	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
+	HostBuf h_seeds[HMP_NUM_MAPGRIDS];
+	cudaEvent_t seeds_event[HMP_NUM_MAPGRIDS] = {nullptr, nullptr, nullptr, nullptr};
+	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
+	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
+	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -565,7 +573,10 @@ HmpContext* hmp_create(int device_id) {
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-	    cudaEventCreate(&ctx->evm) != cudaSuccess ||
+	    cudaEventCreate(&ctx->evm) != cudaSuccess || cudaEventCreateWithFlags(&ctx->seeds_event[0], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->seeds_event[1], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->seeds_event[2], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->seeds_event[3], cudaEventDisableTiming) != cudaSuccess ||
 	    hmp_dev_configure(ctx->max_smem_optin) != cudaSuccess) {
 		set_err("context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
 		delete ctx;
@@ -578,7 +589,12 @@ void hmp_destroy(HmpContext* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&ctx->d_seeds, &ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		ctx->d_seeds[g].release();
+		ctx->h_seeds[g].release();
+		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
+	}
+	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
 	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
@@ -676,6 +692,27 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 	return HMP_OK;
 }
 
+
+// Checks the overflow flag of queued wave fronts; a grid whose frontier overflowed the shared-memory queues is recomputed
+// with the scan kernel (never observed for 200 x 200 windows; kept for correctness on pathological maps).
+static int resolve_wavefronts(HmpContext* ctx) {
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!ctx->wavefront_pending[g]) continue;
+		ctx->wavefront_pending[g] = false;
+		int status = 0;
+		CU(cudaMemcpyAsync(&status, ctx->d_seeds[g].p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		if (status) {
+			const size_t n = (size_t)ctx->size_x * ctx->size_y;
+			CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p, ctx->size_x, ctx->size_y, (const int*)ctx->d_seeds[g].p + 1,
+			                            ctx->n_seeds[g], (float*)ctx->d_mapgrids.p + (size_t)g * n, ctx->stream));
+			ctx->launches++;
+			CU(cudaStreamSynchronize(ctx->stream));
+		}
+	}
+	return HMP_OK;
+}
+
 // Host part of base_local_planner::MapGrid::setTargetCells / setLocalGoal [RECALLED, SURVEY App. B]: densify the plan
 // to the costmap resolution (adjustPlanResolution) and collect the seed cells; the wave front itself runs on the device.
 int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, int32_t n_plan, int32_t local_goal,
@@ -743,15 +780,30 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 		}
 		if (local_goal && goal >= 0) seeds.push_back(goal);
 	}
-	int rc = ctx->d_seeds.ensure(std::max<size_t>(1, seeds.size()) * sizeof(int));
+	// per-slot staging so that the four grids of a cycle queue on the stream without a host synchronisation:
+	// [0] overflow status, [1..] seed cells
+	const size_t need = (1 + std::max<size_t>(1, seeds.size())) * sizeof(int);
+	int rc = ctx->d_seeds[grid].ensure(need);
 	if (rc) return rc;
+	if (need > ctx->h_seeds[grid].cap) {
+		CU(cudaStreamSynchronize(ctx->stream));
+		if ((rc = ctx->h_seeds[grid].ensure(need * 2))) return rc;
+	} else if (ctx->seeds_event_valid[grid]) {
+		CU(cudaEventSynchronize(ctx->seeds_event[grid]));   // previous upload from this staging buffer has been consumed
+	}
+	int* hs = (int*)ctx->h_seeds[grid].p;
+	hs[0] = 0;
+	if (!seeds.empty()) std::memcpy(hs + 1, seeds.data(), seeds.size() * sizeof(int));
 	cudaStream_t st = ctx->stream;
-	CU(cudaStreamSynchronize(st));
-	if (!seeds.empty()) CU(cudaMemcpyAsync(ctx->d_seeds.p, seeds.data(), seeds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-	CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p, sx, sy, (const int*)ctx->d_seeds.p, (int)seeds.size(),
-	                            (float*)ctx->d_mapgrids.p + (size_t)grid * n, st));
+	int* dsd = (int*)ctx->d_seeds[grid].p;
+	CU(cudaMemcpyAsync(dsd, hs, need, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(ctx->seeds_event[grid], st));
+	ctx->seeds_event_valid[grid] = true;
+	float* out = (float*)ctx->d_mapgrids.p + (size_t)grid * n;
+	CU(hmp_dev_launch_wavefront_queue((const uint8_t*)ctx->d_costmaps.p, sx, sy, dsd + 1, (int)seeds.size(), out, dsd, st));
 	ctx->launches++;
-	CU(cudaStreamSynchronize(st));   // `seeds` is a stack-owned staging buffer
+	ctx->wavefront_pending[grid] = true;
+	ctx->n_seeds[grid] = (int)seeds.size();   // overflow status is checked (and the scan kernel re-run) before the next plan
 	ctx->have_grid[grid] = true;
 	ctx->hv_prev[grid] = highest_valid_cost_prev;
 	ctx->last_valid = false;
@@ -764,6 +816,10 @@ int hmp_get_mapgrid(HmpContext* ctx, int32_t grid, double* target_dist_out) {
 		return HMP_E_INVALID;
 	}
 	CU(cudaSetDevice(ctx->device));
+	{
+		int rc = resolve_wavefronts(ctx);
+		if (rc) return rc;
+	}
 	const size_t n = (size_t)ctx->size_x * ctx->size_y;
 	std::vector<float> tmp(n);
 	CU(cudaMemcpyAsync(tmp.data(), (const float*)ctx->d_mapgrids.p + (size_t)grid * n, n * sizeof(float), cudaMemcpyDeviceToHost,
@@ -958,6 +1014,7 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	if ((rc = resolve_wavefronts(ctx))) return rc;
 	int T = compute_steps(ctx->params.general, std::hypot(world->vel_x, world->vel_y), world->vel_th);
 	if (T < 1 || T > HMP_MAX_STEPS) {
 		set_err("rollout has %d steps, supported 1..%d", T, HMP_MAX_STEPS);

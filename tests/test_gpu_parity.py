@@ -534,3 +534,26 @@ def test_batch_64_scenes(planner):
         planner.set_scene(keep[s])
         r, _ = planner.plan(keep[s].world, smp, want_poses=False)
         assert r.best_index == res[s].best_index and r.best_total == res[s].best_total
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# closed-loop replay (BASELINE config 5): init -> move -> adjust -> stop with moving people
+# ---------------------------------------------------------------------------------------------------------------
+def test_closed_loop_replay(planner):
+    from humap_local_planner_b200 import replay
+
+    def check(params, sc, smp, res):
+        ref = ob.plan(params, sc, smp, early_exit=False, want=("totals",))
+        valid = np.sort(ref["totals"][ref["totals"] >= 0])
+        close = len(valid) > 1 and (valid[1] - valid[0]) <= 1e-4 * abs(valid[0])
+        return ref["result"].best_index == res.best_index or close
+
+    planner.set_precision(False)
+    log = replay.run_replay(planner, n_cycles=400, on_plan=check, on_plan_every=10)
+    s = replay.summarize(log)
+    # the state machine walks init -> move -> adjust -> stop and starts over with the next goal
+    seq = s["state_sequence_head"]
+    assert seq[:4] == ["init", "move", "adjust", "stop"] or seq[:3] == ["move", "adjust", "stop"], seq
+    assert s["goals_reached"] >= 1 and s["move_cycles"] >= 50
+    assert s["parity_checked"] >= 5 and s["parity_mismatch"] == 0, s
+    assert s["p99_cycle_ms"] < 50.0
