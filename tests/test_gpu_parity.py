@@ -549,7 +549,7 @@ def test_closed_loop_replay(planner):
         return ref["result"].best_index == res.best_index or close
 
     planner.set_precision(False)
-    log = replay.run_replay(planner, n_cycles=400, on_plan=check, on_plan_every=10)
+    log = replay.run_replay(planner, n_cycles=700, on_plan=check, on_plan_every=20)
     s = replay.summarize(log)
     # the state machine walks init -> move -> adjust -> stop and starts over with the next goal
     seq = s["state_sequence_head"]
