@@ -17,6 +17,12 @@
 #define HMP_DEV_MAX_KERNEL_PTS 9   /* centre + 8 offsets (RECTANGLE kernel) */
 #define HMP_WARPS_PER_BLOCK 8
 #define HMP_THREADS_PER_BLOCK (32 * HMP_WARPS_PER_BLOCK)
+#ifndef HMP_LOCKSTEP
+#define HMP_LOCKSTEP 1
+#endif
+#ifndef HMP_LOCKSTEP_EXTRA
+#define HMP_LOCKSTEP_EXTRA 0
+#endif
 #ifndef HMP_MIN_BLOCKS
 #define HMP_MIN_BLOCKS 2
 #endif
