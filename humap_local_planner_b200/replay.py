@@ -154,6 +154,8 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
             err = head_err if state == "init" else _wrap(gyaw - th)
             want = math.copysign(min(max(abs(err), L.min_vel_theta), L.max_vel_theta), err)
             want = math.copysign(min(abs(want), math.sqrt(2.0 * L.acc_lim_theta * abs(err))), err)
+            if state == "adjust" and abs(err) <= 0.5 * YAW_TOL:
+                want = 0.0     # inside the yaw tolerance: stop rotating (LatchedStopRotateController::isGoalReached)
             cmd_th = min(max(want, vth - L.acc_lim_theta * period), vth + L.acc_lim_theta * period)
             cmd_x = max(vx - L.acc_lim_x * period, 0.0)
         # ---- apply the command for one period (computeNextPoseBaseVel), move the people ----------------------------
