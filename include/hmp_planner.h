@@ -270,7 +270,7 @@ int hmp_abi_version(void);
 int hmp_set_params(HmpContext* ctx, const HmpParams* params);
 
 /* Arithmetic of the per-object loops (static / dynamic interaction forces, fuzzy inference): 0 = FP32 (default,
- * the fast path), 1 = FP64 (parity mode: isolates restatement errors from FP32 rounding; several times slower).
+ * the fast path), 1 = FP64 (parity mode: reproduces the FP64 reference to rounding noise; about 2x slower).
  * Pose integration, twist / limit arithmetic, cell indexing and the weighted total are FP64 in both modes. */
 int hmp_set_precision(HmpContext* ctx, int32_t fp64);
 
