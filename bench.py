@@ -14,8 +14,9 @@ argmin selected. The default workload is BASELINE.json configs[2] ("crowd stress
          result out: hmp_set_costmap + 4 x hmp_set_mapgrid + hmp_set_footprint + hmp_plan (wall clock).
   N > 1  independent scenes, one per rank (scene seed = rank), no collective on the data path: weak scaling.
 
-`--impl reference` times the CPU restatement of the reference path (oracle/, FP64, all host threads) on a
-bounded candidate sample of the same workload.
+`--impl reference` times the reference's CPU implementation of the path (oracle/_ref: its own sources compiled in
+place; falls back to the oracle restatement if that library is absent), FP64, all host threads, on a bounded candidate
+sample of the same workload.
 """
 from __future__ import annotations
 
@@ -85,17 +86,23 @@ class ClockSampler:
 
 
 def cpu_baseline(cfg, scene, params, sampling, seconds_budget=12.0):
-    """The oracle (CPU restatement of the reference path) on a bounded sample, all host threads."""
+    """The reference path on the host cores, bounded sample, all host threads.
+
+    kind "reference": oracle/_ref/libhmp_ref.so -- the reference's own first-party sources for the path (generator, SFM,
+    World, FIS, conductor, critics) compiled in place against the stand-in third-party headers of oracle/ref_shim/ --
+    when that library was built (it travels to the GPU box with the snapshot); kind "port": the oracle restatement."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     import concurrent.futures as cf
     cores = os.cpu_count() or 1
+    impl = "ref" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhmp_ref.so")) else "oracle"
+    kind = "reference" if impl == "ref" else "port"
     Cn = ob.num_candidates(sampling)
     # calibrate on a few candidates, then size the sample for ~seconds_budget of wall time
     probe = np.unique(np.linspace(0, Cn - 1, 4).astype(int))
     t0 = time.perf_counter()
     for i in probe:
-        ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",))
+        ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",), impl=impl)
     per = (time.perf_counter() - t0) / len(probe)
     n = int(min(Cn, max(cores, seconds_budget / per * cores)))
     idx = np.unique(np.linspace(0, Cn - 1, n).astype(int))
@@ -103,20 +110,22 @@ def cpu_baseline(cfg, scene, params, sampling, seconds_budget=12.0):
 
     def work(ch):
         for i in ch:
-            ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",))
+            ob.plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), want=("totals",), impl=impl)
         return len(ch)
 
     t0 = time.perf_counter()
     with cf.ThreadPoolExecutor(cores) as ex:
         done = sum(ex.map(work, chunks))
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    what = ("reference first-party sources compiled in place (oracle/_ref, stand-in third-party headers)" if impl == "ref"
+            else "oracle restatement (oracle/hmp_oracle.cpp)")
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{done} of {Cn} candidates of {cfg.name} (evenly spaced over the sampling grid), {dt:.1f} s wall, "
-                      f"single-thread rate {1.0 / per:.1f} candidates/s"}, dt, done
+                      f"single-thread rate {1.0 / per:.1f} candidates/s; {what}"}, dt, done
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the CPU restatement of the reference path, bounded sample per step, rank 0 only."""
+    """`--impl reference`: the reference's CPU path (oracle/_ref, else the oracle port), bounded sample per step, rank 0 only."""
     if rank != 0:
         return
     from humap_local_planner_b200 import scenes

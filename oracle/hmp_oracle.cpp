@@ -2182,4 +2182,33 @@ double orc_passing_speed(double distance, double speed, double min_dist, double 
 	return passingSpeedDiscomfort(distance, speed, min_dist, max_speed);
 }
 
+// ---- hooks for the third-party stand-ins of the oracle/_ref build (oracle/ref_shim/shim_hooks.h): the compiled-in-place
+// reference sources call these where the real build would call social_nav_utils / base_local_planner ----------------
+double orc_tp_gaussian_angle(double x, double mean, double variance, int normalize) {
+	return calculateGaussianAngle(x, mean, variance, normalize != 0);
+}
+double orc_tp_personal_space(double xp, double yp, double yawp, double cxx, double cxy, double cyx, double cyy, double var_front,
+                             double var_rear, double var_side, double xr, double yr) {
+	return personalSpaceIntrusion(xp, yp, yawp, cxx, cxy, cyx, cyy, var_front, var_rear, var_side, xr, yr);
+}
+double orc_tp_formation_space(double xg, double yg, double yawg, double var_x, double var_y, double cxx, double cxy, double cyy,
+                              double xr, double yr) {
+	return formationSpaceIntrusion(xg, yg, yawg, var_x, var_y, cxx, cxy, cyy, xr, yr);
+}
+double orc_tp_heading_disturbance(double xp, double yp, double yawp, double cxx, double cxy, double cyy, double xr, double yr,
+                                  double yawr, double vxr, double vyr, double person_radius, double fov_person,
+                                  double robot_circumradius, double max_speed) {
+	return headingDirectionDisturbance(xp, yp, yawp, cxx, cxy, cyy, xr, yr, yawr, vxr, vyr, person_radius, fov_person,
+	                                   robot_circumradius, max_speed);
+}
+double orc_tp_passing_speed(double distance, double speed, double min_dist, double max_speed) {
+	return passingSpeedDiscomfort(distance, speed, min_dist, max_speed);
+}
+double orc_tp_footprint_cost(const uint8_t* cells, int size_x, int size_y, double origin_x, double origin_y, double resolution,
+                             double x, double y, double theta, const double* spec_xy, int n_spec) {
+	Costmap cm{cells, size_x, size_y, origin_x, origin_y, resolution};
+	std::vector<double> spec(spec_xy, spec_xy + 2 * n_spec);
+	return worldModelFootprintCost(cm, x, y, theta, spec);
+}
+
 }  // extern "C"

@@ -1,0 +1,3 @@
+// Stand-in: all geometry_msgs structs live in Pose.h
+#pragma once
+#include <geometry_msgs/Pose.h>

@@ -13,8 +13,10 @@ from humap_local_planner_b200.capi import (HmpParams, HmpWorld, HmpSampling, Hmp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = os.path.join(ROOT, "oracle", "_build", "libhmp_oracle.so")
+_REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libhmp_ref.so")
 _d, _i = C.c_double, C.c_int32
 _lib = None
+_ref_lib = None
 
 
 class OrcPlanInput(C.Structure):
@@ -60,6 +62,27 @@ def lib() -> C.CDLL:
         _lib.orc_behaviour_strength_exp.argtypes = [_d, _d, _d, _d]
         _lib.orc_passing_speed.argtypes = [_d, _d, _d, _d]
     return _lib
+
+
+def ref_available() -> bool:
+    """True when oracle/_ref/libhmp_ref.so (the reference's own sources compiled against oracle/ref_shim) exists or can
+    be built here (needs /root/reference; on the GPU box only the prebuilt library is used)."""
+    return os.path.exists(_REF_LIB) or os.path.isdir("/root/reference/src")
+
+
+def ref_lib() -> C.CDLL:
+    global _ref_lib
+    if _ref_lib is None:
+        lib()  # libhmp_oracle.so first: the stand-ins' orc_tp_* hooks resolve against it
+        if not os.path.exists(_REF_LIB):
+            subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+        _ref_lib = C.CDLL(_REF_LIB)
+        _ref_lib.ref_plan.argtypes = [C.POINTER(OrcPlanInput), C.POINTER(OrcPlanOutput)]
+        _ref_lib.ref_plan.restype = C.c_int
+        _ref_lib.ref_fis_process.argtypes = [_d, _d, _d, _d, C.c_void_p]
+        _ref_lib.ref_fis_process.restype = None
+        _ref_lib.ref_num_candidates.argtypes = [C.POINTER(HmpSampling), C.c_int]
+    return _ref_lib
 
 
 def _p(a):
@@ -110,9 +133,12 @@ def score_trajectory(params: HmpParams, scene: Scene, sampling: HmpSampling, pos
 
 
 def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, early_exit: bool = False,
-         cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1):
-    """Runs orc_plan and returns a dict of numpy arrays (+ 'result': HmpResult)."""
+         cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1,
+         impl: str = "oracle"):
+    """Runs orc_plan (impl="oracle") or ref_plan (impl="ref": the reference's own sources, oracle/ref_driver.cpp) and
+    returns a dict of numpy arrays (+ 'result': HmpResult)."""
     L = lib()
+    fn = L.orc_plan if impl == "oracle" else ref_lib().ref_plan
     ex = None
     n_extra = 0
     if extra is not None:
@@ -147,7 +173,7 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     if forces_candidate >= 0:
         arrs["forces"] = np.zeros((T, 8))
         out.forces = _p(arrs["forces"])
-    rc = L.orc_plan(C.byref(inp), C.byref(out))
+    rc = fn(C.byref(inp), C.byref(out))
     assert rc == 0
     res = HmpResult()
     C.memmove(C.byref(res), C.byref(out.result), C.sizeof(HmpResult))
