@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--cfg", default="cfg2")
     ap.add_argument("--fis", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precise", type=int, default=0, help="1: FP64 object loops (hmp_set_precision), the exact-parity mode")
+    ap.add_argument("--precise", type=int, default=2, help="hmp_set_precision mode: 0 FP32 object loops, 1 FP64 (exact-parity mode), 2 FP32 sweep + FP64 refinement of the leaders")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -204,7 +204,7 @@ def main():
     params = scenes.make_params(cfg, fis=bool(args.fis))
     sampling = scenes.make_sampling(cfg)
     pl = Planner(local_rank)
-    pl.set_precision(bool(args.precise))
+    pl.set_precision(int(args.precise))
     pl.set_params(params)
 
     def full_cycle():
@@ -302,7 +302,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * C * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64" if args.precise else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {0: "f32", 1: "f64", 2: "f32 sweep + f64 refinement of the leaders"}[int(args.precise)], "data": "synthetic",
             "config": {"workload": _workload_name(cfg, args), "candidates": C, "steps_per_rollout": T,
                        "parallelism": f"independent scenes x{world}, one per rank, no collective",
                        "l2": "flushed with a 256 MiB write between timed iterations", "timing": "CUDA events on the launching stream"},

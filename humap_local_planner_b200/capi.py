@@ -119,6 +119,7 @@ ABI_SYMBOLS = (
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
+    "hmp_set_refinement", "hmp_last_num_leaders",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -168,6 +169,10 @@ def load_library() -> C.CDLL:
     lib.hmp_get_mapgrid.argtypes = [C.c_void_p, _i, C.c_void_p]
     lib.hmp_get_mapgrid.restype = C.c_int
     lib.hmp_set_precision.restype = C.c_int
+    lib.hmp_set_refinement.argtypes = [C.c_void_p, _d, _i]
+    lib.hmp_set_refinement.restype = C.c_int
+    lib.hmp_last_num_leaders.argtypes = [C.c_void_p]
+    lib.hmp_last_num_leaders.restype = C.c_int
     lib.hmp_launch_count.restype = C.c_int64
     lib.hmp_launch_count.argtypes = [C.c_void_p]
     for name in ("hmp_set_params", "hmp_set_costmap", "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan",
@@ -234,8 +239,15 @@ class Planner:
     def set_params(self, params: HmpParams):
         self._check(self._lib.hmp_set_params(self._ctx, C.byref(params)))
 
-    def set_precision(self, fp64: bool):
-        self._check(self._lib.hmp_set_precision(self._ctx, 1 if fp64 else 0))
+    def set_precision(self, mode):
+        """False / 0: FP32 object loops; True / 1: FP64 (parity mode); 2: FP32 sweep + FP64 refinement of the leaders."""
+        self._check(self._lib.hmp_set_precision(self._ctx, int(mode)))
+
+    def set_refinement(self, rel_window: float = 0.02, max_leaders: int = 256):
+        self._check(self._lib.hmp_set_refinement(self._ctx, float(rel_window), int(max_leaders)))
+
+    def last_num_leaders(self) -> int:
+        return int(self._lib.hmp_last_num_leaders(self._ctx))
 
     def set_costmap(self, cells: np.ndarray, origin_x: float, origin_y: float, resolution: float):
         cells = np.ascontiguousarray(cells, dtype=np.uint8)

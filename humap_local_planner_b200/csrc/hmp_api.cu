@@ -29,6 +29,13 @@ extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_str
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
+                                                      int32_t* leaders, int32_t* count, int n_scenes, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
+                                                    const double* r_costs, const double* r_seeds, const double* r_poses,
+                                                    const int32_t* r_nposes, double* totals_full, double* best_out, double* o_costs,
+                                                    double* o_seeds, double* o_poses, double* o_total, int32_t* o_nposes,
+                                                    int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
@@ -141,7 +148,10 @@ struct HmpContext {
 	std::vector<double> footprint;
 	std::vector<uint8_t> h_cells;   // host copy of the single-scene costmap (seed test of the device wave front)
 	bool have_footprint = false;
-	int precise = 0;
+	int precise = 2;                 // 0 FP32, 1 FP64, 2 (default) FP32 sweep + FP64 refinement of the leaders
+	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
+	int refine_max_leaders = 256;    // per scene (single-scene plans); batches use min(this, 32)
+	int last_n_leaders = 0;
 
 	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
 	HostBuf h_seeds[HMP_NUM_MAPGRIDS];
@@ -149,7 +159,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -515,7 +525,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		}
 	}
 	int bps = 0;
-	CU(hmp_dev_occupancy(smem, ctx->precise, &bps));
+	CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
 		return HMP_E_CUDA;
@@ -595,7 +605,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	ctx->h_out.release();
@@ -895,7 +905,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
 	A.costmap_stride = ctx->costmap_stride;
 	A.costmap_in_smem = in_smem;
-	A.precise = ctx->precise;
+	A.precise = (ctx->precise == 1) ? 1 : 0;
 	A.mapgrids = (const float*)ctx->d_mapgrids.p;
 	A.n_work = C;
 	A.totals = (double*)ctx->d_totals.p;
@@ -912,21 +922,64 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes, ctrl, cl.total, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 
-	// winner's detail pass: one warp per scene re-runs the best candidate with write-back
 	KernelArgs B = A;
 	double* det = (double*)ctx->d_detail.p;
-	B.n_work = 1;
-	B.use_best_index = 1;
 	B.d_costs = det;
 	B.d_seeds = det + (size_t)NS * HMP_NUM_COSTS;
 	B.d_poses = B.d_seeds + (size_t)NS * 3;
 	B.totals = B.d_poses + (size_t)NS * T * 3;
 	B.d_nposes = (int32_t*)(B.totals + NS);
 	B.d_forces = nullptr;
-	CU(hmp_dev_launch_plan(&B, 1, 1, smem, st));
-	ctx->launches++;
+	if (ctx->precise != 2) {
+		// winner's detail pass: one warp per scene re-runs the best candidate with write-back
+		B.n_work = 1;
+		B.use_best_index = 1;
+		CU(hmp_dev_launch_plan(&B, 1, 1, smem, st));
+		ctx->launches++;
+		ctx->last_n_leaders = 0;
+	} else {
+		// selection refinement: leaders of the FP32 sweep -> FP64 rollouts -> winner among the refined totals
+		const int K = (NS == 1) ? ctx->refine_max_leaders : std::min(ctx->refine_max_leaders, 32);
+		const bool want_poses = (NS == 1);
+		const size_t nk = (size_t)NS * K;
+		const size_t r_doubles = nk * (HMP_NUM_COSTS + 3 + 1) + (want_poses ? nk * T * 3 : 0);
+		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + NS) * sizeof(int32_t);
+		if ((rc = ctx->d_refine.ensure(r_bytes))) return rc;
+		double* r_costs = (double*)ctx->d_refine.p;
+		double* r_seeds = r_costs + nk * HMP_NUM_COSTS;
+		double* r_totals = r_seeds + nk * 3;
+		double* r_poses = want_poses ? r_totals + nk : nullptr;
+		int32_t* r_leaders = (int32_t*)((double*)ctx->d_refine.p + r_doubles);
+		int32_t* r_nposes = r_leaders + nk;
+		int32_t* r_count = r_nposes + nk;
+		CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count, NS, st));
+		KernelArgs Rf = A;
+		Rf.precise = 1;
+		Rf.cand_list = r_leaders;
+		Rf.cand_list_stride = K;
+		Rf.n_work = K;
+		Rf.use_best_index = 0;
+		Rf.d_costs = r_costs;
+		Rf.d_seeds = r_seeds;
+		Rf.d_poses = r_poses;
+		Rf.totals = r_totals;
+		Rf.d_nposes = r_nposes;
+		Rf.d_forces = nullptr;
+		// few candidates, many SMs: spread them (2 per block for a single scene) to shorten the serial FP64 rollout
+		Rf.warps_per_ticket = (NS == 1) ? 2 : HMP_WARPS_PER_BLOCK;
+		const int wpt = Rf.warps_per_ticket;
+		const int rblocks = (K + wpt - 1) / wpt;
+		CU(hmp_dev_launch_plan(&Rf, rblocks, 1, smem, st));
+		CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
+		                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, st));
+		ctx->launches += 3;
+		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	}
 	CU(cudaEventRecord(ctx->ev1, st));
 	CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
+	if (ctx->precise == 2)   // the refinement may have replaced (best total, best index) after the control-block snapshot
+		CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes + cl.off_best, ctrl + cl.off_best, (size_t)NS * 2 * sizeof(double),
+		                   cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	float ms = 0.f;
 	CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1183,7 +1236,7 @@ int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n, do
 	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;
 	A.costmap_stride = ctx->costmap_stride;
 	A.costmap_in_smem = in_smem;
-	A.precise = ctx->precise;
+	A.precise = (ctx->precise == 1) ? 1 : 0;
 	A.mapgrids = (const float*)ctx->d_mapgrids.p;
 	A.cand_list = d_idx;
 	A.n_work = n;
@@ -1307,25 +1360,38 @@ int hmp_debug_fis(HmpContext* ctx, const double* in4, int32_t n, double* out2) {
 	double* dout = din + (size_t)n * 4;
 	cudaStream_t st = ctx->stream;
 	CU(cudaMemcpyAsync(din, in4, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-	CU(hmp_dev_launch_fis(din, n, dout, ctx->precise, st));
+	CU(hmp_dev_launch_fis(din, n, dout, ctx->precise == 1, st));
 	ctx->launches++;
 	CU(cudaMemcpyAsync(out2, dout, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return HMP_OK;
 }
 
-// 0 (default): FP32 object loops and FIS -- the fast path the benchmarks time. 1: the same kernel instantiated
-// with FP64 object loops and FIS (vertex quantisation included) -- parity mode used to separate restatement
-// errors from FP32 rounding.
+// 0: FP32 object loops and FIS -- the fast path. 1: the same kernel instantiated with FP64 object loops and
+// FIS (vertex quantisation included) -- parity mode used to separate restatement errors from FP32 rounding.
+// 2 (default): FP32 sweep over all candidates, then the leaders (hmp_set_refinement) are rolled out again in FP64 and the winner
+// is chosen among the refined totals: the selection, the command and the winner's record are those of the FP64 path.
 int hmp_set_precision(HmpContext* ctx, int32_t fp64) {
 	if (!ctx) {
 		set_err("null context");
 		return HMP_E_INVALID;
 	}
-	ctx->precise = fp64 ? 1 : 0;
+	ctx->precise = (fp64 == 2) ? 2 : (fp64 ? 1 : 0);
 	ctx->last_valid = false;
 	return HMP_OK;
 }
+
+int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders) {
+	if (!ctx || !(rel_window >= 0.0) || max_leaders < 1 || max_leaders > 4096) {
+		set_err("bad refinement arguments (window >= 0, 1 <= max_leaders <= 4096)");
+		return HMP_E_INVALID;
+	}
+	ctx->refine_window = rel_window;
+	ctx->refine_max_leaders = (max_leaders + 7) / 8 * 8;
+	return HMP_OK;
+}
+
+int hmp_last_num_leaders(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders : -1; }
 
 int64_t hmp_launch_count(HmpContext* ctx) { return ctx ? ctx->launches : 0; }
 

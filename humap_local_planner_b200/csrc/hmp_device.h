@@ -157,7 +157,7 @@ struct KernelArgs {
 	uint32_t costmap_stride;
 	int32_t costmap_in_smem;
 	int32_t precise;                 /* 1: object loops and the FIS in FP64 (parity mode), 0: FP32 (fast mode) */
-	int32_t _padk;
+	int32_t cand_list_stride;        /* scene s reads cand_list + s * cand_list_stride (0: one list for all scenes) */
 	const float* mapgrids;           /* [n_scenes][4][size_y * size_x]                            */
 	/* selection */
 	const int32_t* cand_list;        /* explicit candidate indices (detail mode) or null          */
@@ -174,6 +174,9 @@ struct KernelArgs {
 	double* d_poses;                 /* [n_work][T][3]                                             */
 	double* d_forces;                /* [n_work][T][8] or null                                     */
 	int32_t* d_nposes;               /* [n_work] poses recorded (T, or fewer when the generator rejected) */
+	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
+	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
+	int32_t _padt;
 };
 
 #endif

@@ -269,10 +269,20 @@ int hmp_abi_version(void);
  *      setXShift calls of updateLocalCosts (:1054-1141) ----------------------------------------- */
 int hmp_set_params(HmpContext* ctx, const HmpParams* params);
 
-/* Arithmetic of the per-object loops (static / dynamic interaction forces, fuzzy inference): 0 = FP32 (default,
- * the fast path), 1 = FP64 (parity mode: reproduces the FP64 reference to rounding noise; about 2x slower).
- * Pose integration, twist / limit arithmetic, cell indexing and the weighted total are FP64 in both modes. */
+/* Arithmetic of the per-object loops (static / dynamic interaction forces, fuzzy inference): 0 = FP32 (the fast
+ * path), 1 = FP64 (parity mode: reproduces the FP64 reference to rounding noise; about 2x slower),
+ * 2 (default) = FP32 sweep + FP64 refinement: all candidates are ranked in FP32, the leaders (valid candidates whose total is
+ * within the window of hmp_set_refinement of the best) are rolled out and scored again in FP64, and the winner is the
+ * first strict minimum of the refined totals -- the selection, the seed twist, the poses and the critic values returned
+ * in HmpResult are then those of the FP64 path at a few percent of extra time.
+ * Pose integration, twist / limit arithmetic, cell indexing and the weighted total are FP64 in every mode. */
 int hmp_set_precision(HmpContext* ctx, int32_t fp64);
+/* Mode 2 only: relative window above the best FP32 total (default 0.02) and the cap on leaders per scene (default 256,
+ * rounded up to a multiple of 8; batches use at most 32). If more candidates fall inside the window it is halved until
+ * they fit. No reference counterpart. */
+int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders);
+/* Leaders re-scored in FP64 by the last plan of scene 0 (0 in modes 0 / 1), -1 if there is no plan. */
+int hmp_last_num_leaders(HmpContext* ctx);
 
 /* Replaces the costmap_2d::Costmap2D* every critic holds (row-major, index = my * size_x + mx). */
 int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y,

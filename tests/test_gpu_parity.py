@@ -500,6 +500,7 @@ def test_parameter_variants(planner, mutate, precise):
 # batched scenes (BASELINE config 4): one launch over n scenes == n single-scene cycles
 # ---------------------------------------------------------------------------------------------------------------
 def test_batched_scenes_equal_single_cycles(planner):
+    planner.set_precision(False)
     cfg = scenes.CONFIGS["cfg3"]
     params = scenes.make_params(cfg)
     smp = scenes.make_sampling(cfg)
@@ -561,6 +562,7 @@ def test_cycle_with_device_wavefront_equals_uploaded_grids(planner):
 def test_batch_64_scenes(planner):
     """A slice of BASELINE config 4 (batched independent scenes, 4k candidates each): every scene's argmin equals the
     argmin of its explored totals, and sampled scenes equal their single-scene cycle."""
+    planner.set_precision(False)
     cfg = scenes.CONFIGS["cfg3"]
     params = scenes.make_params(cfg)
     smp = scenes.make_sampling(cfg)
@@ -601,7 +603,7 @@ def test_batch_64_scenes(planner):
 # ---------------------------------------------------------------------------------------------------------------
 # closed-loop replay (BASELINE config 5): init -> move -> adjust -> stop with moving people
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precise", [False, True], ids=["fp32", "fp64"])
+@pytest.mark.parametrize("precise", [False, True, 2], ids=["fp32", "fp64", "refine"])
 def test_closed_loop_replay(planner, precise):
     from humap_local_planner_b200 import replay
     notes = []
@@ -629,7 +631,7 @@ def test_closed_loop_replay(planner, precise):
     assert s["goals_reached"] >= 1 and s["move_cycles"] >= 50
     assert s["parity_checked"] >= 5
     if precise:
-        # FP64 object loops: the device selection IS the oracle's selection
+        # FP64 object loops (or FP32 sweep + FP64 refinement of the leaders): the device selection IS the oracle's selection
         assert s["parity_mismatch"] == 0, notes
     else:
         # FP32 object loops: pose noise of ~1e-6 m occasionally moves a footprint vertex or the end pose into the neighbouring
@@ -639,3 +641,87 @@ def test_closed_loop_replay(planner, precise):
         for rb, tr, gb, tg, _ in notes:
             assert tg is not None and (tg - tr) <= 0.02 * abs(tr), notes
     assert s["p99_cycle_ms"] < 50.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# precision mode 2: FP32 sweep + FP64 refinement of the leaders
+# ---------------------------------------------------------------------------------------------------------------
+def _refined_vs_oracle(planner, name, seed, full_totals):
+    cfg, sc, params, smp = _setup(planner, name, seed, precise=2)
+    res, poses = planner.plan(sc.world, smp)
+    n_lead = planner.last_num_leaders()
+    g = planner.explored_totals(res.n_candidates)
+    planner.set_precision(False)
+    valid = np.where(full_totals >= 0)[0]
+    if len(valid) == 0:
+        assert res.status == 1 and res.best_index == -1
+        return
+    order = valid[np.argsort(full_totals[valid], kind="stable")]
+    best = int(order[0])
+    top2_close = len(order) > 1 and (full_totals[order[1]] - full_totals[best]) <= 1e-4 * abs(full_totals[best])
+    assert 1 <= n_lead <= 256
+    assert res.best_index == best or top2_close, (res.best_index, best)
+    # the record of the winner is the FP64 path's: total, seed twist, poses and critics agree to rounding noise
+    o = ob.plan_sampled(params, sc, smp, [res.best_index])
+    assert abs(res.best_total - o["totals"][0]) <= 1e-6 * abs(o["totals"][0])
+    assert np.abs(poses - o["poses"][0]).max() < 1e-8
+    assert np.abs(np.array([res.xv, res.yv, res.thetav]) - o["seeds"][0]).max() < 1e-9
+    assert np.allclose(np.array(res.costs), o["costs"][0], rtol=1e-5, atol=1e-7, equal_nan=True)
+    # explored totals: refined entries replaced the FP32 ones
+    assert abs(g[res.best_index] - res.best_total) == 0.0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_refined_selection_cfg0(planner, seed):
+    cfg = scenes.CONFIGS["cfg0"]
+    full = ob.plan(scenes.make_params(cfg), scenes.make_scene(cfg, seed), scenes.make_sampling(cfg), want=("totals",))["totals"]
+    _refined_vs_oracle(planner, "cfg0", seed, full)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_refined_selection_cfg1_full_grid(planner, seed):
+    cfg = scenes.CONFIGS["cfg1"]
+    full = ob.plan_all_threaded(scenes.make_params(cfg), scenes.make_scene(cfg, seed), scenes.make_sampling(cfg))
+    _refined_vs_oracle(planner, "cfg1", seed, full)
+
+
+def test_refinement_window_and_cap(planner):
+    """More candidates inside the window than the cap: the window shrinks until they fit; the winner is still refined."""
+    cfg, sc, params, smp = _setup(planner, "cfg1", 1, precise=2)
+    planner.set_refinement(0.5, 16)
+    res_small, _ = planner.plan(sc.world, smp)
+    n_small = planner.last_num_leaders()
+    planner.set_refinement(0.02, 256)
+    res, _ = planner.plan(sc.world, smp)
+    n = planner.last_num_leaders()
+    planner.set_precision(False)
+    assert 1 <= n_small <= 16 and n_small <= n <= 256
+    assert res_small.best_index == res.best_index and res_small.best_total == res.best_total
+    # FP32-only selection of the same cycle for comparison: same winner here, total differs by FP32 rounding only
+    res32, _ = planner.plan(sc.world, smp)
+    assert planner.last_num_leaders() == 0
+    assert abs(res32.best_total - res.best_total) <= 1e-4 * abs(res.best_total)
+
+
+def test_refined_batch_equals_single_cycles(planner):
+    """hmp_plan_batch in mode 2: per-scene leaders lists, same winners as scene-by-scene refined plans."""
+    cfg = scenes.CONFIGS["cfg3"]
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    scs = [scenes.make_scene(cfg, s) for s in range(6)]
+    planner.set_precision(2)
+    planner.set_params(params)
+    singles = []
+    for sc in scs:
+        planner.set_scene(sc)
+        r, _ = planner.plan(sc.world, smp)
+        singles.append((r.best_index, r.best_total))
+    planner.set_scene(scs[0])
+    cells = np.stack([sc.cells for sc in scs])
+    grids = [np.stack([sc.grids[g] for sc in scs]) for g in range(4)]
+    hv = np.array([sc.hv_prev for sc in scs])
+    res = planner.plan_batch([sc.world for sc in scs], cells, grids, smp, hv_prev=hv)
+    planner.set_precision(False)
+    for (bi, bt), r in zip(singles, res):
+        assert r.best_index == bi
+        assert abs(r.best_total - bt) <= 1e-12 * max(1.0, abs(bt))
