@@ -29,6 +29,8 @@ extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_str
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, uint32_t stride, float radius, uint8_t* out,
+                                             int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
                                                       int32_t* leaders, int32_t* count, int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
@@ -152,6 +154,9 @@ struct HmpContext {
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
 	int refine_max_leaders = 256;    // per scene (single-scene plans); batches use min(this, 32)
 	int last_n_leaders = 0;
+	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
+	int dilated_scenes = 0;
+	int prune_obstacle = 1;          // HMP_NO_PRUNE=1 in the environment disables the dilated-map pruning (A/B timing)
 
 	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
 	HostBuf h_seeds[HMP_NUM_MAPGRIDS];
@@ -159,7 +164,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -579,6 +584,7 @@ HmpContext* hmp_create(int device_id) {
 		return nullptr;
 	}
 	ctx->device = device_id;
+	ctx->prune_obstacle = getenv("HMP_NO_PRUNE") ? 0 : 1;
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -605,7 +611,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	ctx->h_out.release();
@@ -625,6 +631,9 @@ int hmp_set_params(HmpContext* ctx, const HmpParams* params) {
 		set_err("sim_time and sim_granularity must be positive");
 		return HMP_E_INVALID;
 	}
+	if (!ctx->have_params || params->costs.occdist_separation != ctx->params.costs.occdist_separation ||
+	    params->costs.occdist_separation_kernel != ctx->params.costs.occdist_separation_kernel)
+		ctx->dilated_dirty = true;
 	ctx->params = *params;
 	ctx->have_params = true;
 	ctx->last_valid = false;
@@ -667,6 +676,7 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
 	ctx->resolution = resolution;
 	ctx->have_costmap = true;
 	ctx->last_valid = false;
+	ctx->dilated_dirty = true;
 	return HMP_OK;
 }
 
@@ -851,6 +861,7 @@ int hmp_set_footprint(HmpContext* ctx, const double* xy, int32_t n_points) {
 	ctx->footprint.assign(xy, xy + 2 * (size_t)n_points);
 	ctx->have_footprint = true;
 	ctx->last_valid = false;
+	ctx->dilated_dirty = true;
 	return HMP_OK;
 }
 
@@ -915,6 +926,24 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.best_out = (double*)(ctrl + cl.off_best);
 
 	CU(cudaEventRecord(ctx->ev0, st));
+	// dilated max-cost map for the exact pruning of the obstacle critic (rebuilt when costmap / footprint / separation change)
+	if (ctx->prune_obstacle && D.scale[HMP_COST_OBSTACLE] != 0.0 && D.n_footprint > 0) {
+		if (ctx->dilated_dirty || ctx->dilated_scenes != NS) {
+			if ((rc = ctx->d_dilated.ensure((size_t)ctx->costmap_stride * NS))) return rc;
+			double r_fp = 0.0, r_k = 0.0;
+			for (int i = 0; i < D.n_footprint; ++i) r_fp = std::max(r_fp, std::hypot(D.footprint_x[i], D.footprint_y[i]));
+			for (int k = 0; k < D.n_kernel_pts; ++k) r_k = std::max(r_k, std::hypot(D.kernel_dx[k], D.kernel_dy[k]));
+			// vertex cells lie within |d| / res + sqrt(2) of the centre cell, rasterised cells within 0.5 of the segment between
+			// two vertex cells: radius (r_fp + r_k) / res + 2 covers them all
+			const float radius = (float)((r_fp + r_k) / D.resolution + 2.0);
+			CU(hmp_dev_launch_dilate((const uint8_t*)ctx->d_costmaps.p, D.size_x, D.size_y, ctx->costmap_stride, radius,
+			                         (uint8_t*)ctx->d_dilated.p, NS, st));
+			ctx->launches++;
+			ctx->dilated_dirty = false;
+			ctx->dilated_scenes = NS;
+		}
+		A.dilated = (const uint8_t*)ctx->d_dilated.p;
+	}
 	CU(hmp_dev_launch_plan(&A, blocks_x, 0, smem, st));
 	ctx->launches++;
 	CU(cudaEventRecord(ctx->evm, st));
@@ -1142,6 +1171,7 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 	if (cells) {
 		CU(cudaMemcpy2DAsync(ctx->d_costmaps.p, ctx->costmap_stride, cells, n, n, n_scenes, cudaMemcpyHostToDevice, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
+		ctx->dilated_dirty = true;
 	} else if (n_scenes > 1) {
 		set_err("hmp_plan_batch needs per-scene costmap cells");
 		return HMP_E_INVALID;

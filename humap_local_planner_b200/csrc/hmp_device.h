@@ -174,6 +174,9 @@ struct KernelArgs {
 	double* d_poses;                 /* [n_work][T][3]                                             */
 	double* d_forces;                /* [n_work][T][8] or null                                     */
 	int32_t* d_nposes;               /* [n_work] poses recorded (T, or fewer when the generator rejected) */
+	const uint8_t* dilated;          /* [n_scenes] maps, stride costmap_stride: max costmap cost over the disc that contains every
+	                                    cell the footprint critic can touch from a centre in that cell (255 outside the map), or
+	                                    null: lets the obstacle critic skip poses that cannot raise its running maximum        */
 	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
 	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
 	int32_t _padt;

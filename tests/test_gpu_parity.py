@@ -728,3 +728,52 @@ def test_refined_batch_equals_single_cycles(planner):
     for (bi, bt), r in zip(singles, res):
         assert r.best_index == bi
         assert abs(r.best_total - bt) <= 1e-12 * max(1.0, abs(bt))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exact pruning of the obstacle critic (dilated max-cost map): results must be bit-identical with and without it
+# ---------------------------------------------------------------------------------------------------------------
+def _pentagon(r=0.3):
+    a = np.arange(5) * 2 * np.pi / 5 + 0.2
+    return np.stack([r * np.cos(a), 0.8 * r * np.sin(a)], axis=1)
+
+
+@pytest.mark.parametrize("name,seed,variant", [("cfg0", 0, "default"), ("cfg0", 1, "sum"), ("cfg1", 1, "default"),
+                                                ("cfg1", 2, "cross"), ("cfg2", 1, "default"), ("cfg0", 3, "pentagon"),
+                                                ("cfg0", 5, "nosep"), ("cfg1", 3, "moved")])
+def test_obstacle_pruning_is_exact(planner, name, seed, variant):
+    import os
+    from humap_local_planner_b200 import Planner
+    cfg = scenes.CONFIGS[name]
+    sc = scenes.make_scene(cfg, seed) if variant != "moved" else scenes.make_scene(cfg, seed, robot_xy=(3.2, -1.1), robot_yaw=-0.8)
+    params = scenes.make_params(cfg)
+    if variant == "sum":
+        params.costs.occdist_sum_scores = 1
+    elif variant == "cross":
+        params.costs.occdist_separation_kernel = 0
+        params.costs.occdist_separation = 0.1
+    elif variant == "nosep":
+        params.costs.occdist_separation = 0.0
+    smp = scenes.make_sampling(cfg)
+    out = []
+    for no_prune in (False, True):
+        if no_prune:
+            os.environ["HMP_NO_PRUNE"] = "1"
+        try:
+            pl = Planner(0) if no_prune else planner
+        finally:
+            os.environ.pop("HMP_NO_PRUNE", None)
+        pl.set_precision(0)
+        pl.set_params(params)
+        pl.set_scene(sc)
+        if variant == "pentagon":
+            pl.set_footprint(_pentagon())
+        res, poses = pl.plan(sc.world, smp)
+        out.append((res.best_index, res.best_total, res.n_valid, list(res.costs), pl.explored_totals(res.n_candidates)))
+        if no_prune:
+            pl.close()
+    a, b = out
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert np.array_equal(np.array(a[3]), np.array(b[3]), equal_nan=True)
+    assert np.array_equal(a[4], b[4])
+    assert (a[4] >= 0).sum() > 0
