@@ -117,6 +117,23 @@ int main() {
 			std::printf("ADAPTER_TEST_FAIL trajectory shape (%f %f -> %f %f)\n", x0, y0, x1, y1);
 			return 1;
 		}
+		// 3) both generators of the reference's pool behind the one adapter generator
+		HmpEquisampled eq = {1, 5, 1, 10, 0.1, 1, 0};
+		gen.setEquisampled(&eq);
+		gen.initialise(w, s, true);
+		base_local_planner::Trajectory result3;
+		result3.cost_ = -7;
+		explored.clear();
+		ok = planner.findBestTrajectory(result3, &explored);
+		const HmpResult& r3 = gen.result();
+		std::printf("pooled: ok=%d cost=%.9f best=%d n=%d social=%d explored=%zu\n", ok, result3.cost_, r3.best_index, r3.n_candidates,
+		            r3.n_social, explored.size());
+		if (!ok || r3.n_social != 12 || r3.n_candidates < 12 + 50 || result3.cost_ != r3.best_total || result3.cost_ > result.cost_ ||
+		    (int)explored.size() != r3.n_generated || result3.getPointsSize() != 35) {
+			std::printf("ADAPTER_TEST_FAIL pooled generators\n");
+			return 1;
+		}
+		gen.setEquisampled(nullptr);
 		std::printf("ADAPTER_TEST_OK\n");
 	} catch (const std::exception& e) {
 		std::printf("ADAPTER_TEST_FAIL exception: %s\n", e.what());

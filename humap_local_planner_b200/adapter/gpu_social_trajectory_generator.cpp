@@ -35,6 +35,10 @@ void GpuSocialTrajectoryGenerator::setFootprint(const std::vector<double>& xy) {
 	check(hmp_set_footprint(ctx_, xy.data(), (int32_t)(xy.size() / 2)), "hmp_set_footprint");
 }
 
+void GpuSocialTrajectoryGenerator::setEquisampled(const HmpEquisampled* eq) {
+	if (hmp_set_equisampled(ctx_, eq) != HMP_OK) throw std::runtime_error(std::string("hmp_set_equisampled: ") + hmp_last_error());
+}
+
 void GpuSocialTrajectoryGenerator::initialise(const HmpWorld& world, const HmpSampling& sampling, bool explore_all) {
 	// deep copy: the reference's generator copies the World too (social_trajectory_generator.cpp:89)
 	obstacles_.assign(world.obstacles, world.obstacles + world.n_obstacles);

@@ -41,6 +41,10 @@ public:
 	void setCostmap(const uint8_t* cells, int size_x, int size_y, double origin_x, double origin_y, double resolution);
 	void setMapGrid(int grid, const double* target_dist, double highest_valid_cost_prev);
 	void setFootprint(const std::vector<double>& xy);
+	/// generator_vel_space_ (humap_planner.cpp:196-203, :1317-1361): when enabled, the equisampled-velocity candidates are
+	/// rolled out and scored on the device in the same pool, after the social ones (generator_list order, :85-88), so this
+	/// one generator stands for both entries of the reference's generator list; nullptr turns them off
+	void setEquisampled(const HmpEquisampled* eq);
 
 	/// SocialTrajectoryGenerator::initialise: stores the cycle's world + sampling; the plan runs lazily
 	void initialise(const HmpWorld& world, const HmpSampling& sampling, bool explore_all = false);

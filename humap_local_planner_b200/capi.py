@@ -110,7 +110,14 @@ class HmpResult(C.Structure):
         ("best_total", _d), ("costs", _d * NUM_COSTS), ("xv", _d), ("yv", _d), ("thetav", _d), ("time_delta", _d),
         ("amplifiers", _d * NUM_AMPLIFIERS), ("highest_valid_cost", _d * NUM_MAPGRIDS),
         ("gpu_ms", _d), ("gpu_ms_select", _d),
+        ("n_social", _i), ("_pad", _i),
     ]
+
+
+class HmpEquisampled(C.Structure):
+    """TrajectoryGeneration's equisampled-velocity generator (humap_config.h:154-174)."""
+    _fields_ = [("enabled", _i), ("vx_samples", _i), ("vy_samples", _i), ("vth_samples", _i), ("min_vel_x", _d),
+                ("continued_acceleration", _i), ("_pad", _i)]
 
 
 # Every symbol include/hmp_planner.h declares (checked by tests/test_capi_symbols.py)
@@ -119,7 +126,7 @@ ABI_SYMBOLS = (
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
-    "hmp_set_refinement", "hmp_last_num_leaders",
+    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -171,6 +178,8 @@ def load_library() -> C.CDLL:
     lib.hmp_set_precision.restype = C.c_int
     lib.hmp_set_refinement.argtypes = [C.c_void_p, _d, _i]
     lib.hmp_set_refinement.restype = C.c_int
+    lib.hmp_set_equisampled.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmp_set_equisampled.restype = C.c_int
     lib.hmp_last_num_leaders.argtypes = [C.c_void_p]
     lib.hmp_last_num_leaders.restype = C.c_int
     lib.hmp_launch_count.restype = C.c_int64
@@ -245,6 +254,10 @@ class Planner:
 
     def set_refinement(self, rel_window: float = 0.02, max_leaders: int = 256):
         self._check(self._lib.hmp_set_refinement(self._ctx, float(rel_window), int(max_leaders)))
+
+    def set_equisampled(self, eq: Optional["HmpEquisampled"]):
+        """Second generator of the pool (equisampled velocities); None turns it off."""
+        self._check(self._lib.hmp_set_equisampled(self._ctx, C.byref(eq) if eq is not None else None))
 
     def last_num_leaders(self) -> int:
         return int(self._lib.hmp_last_num_leaders(self._ctx))

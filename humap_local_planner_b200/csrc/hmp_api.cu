@@ -154,6 +154,8 @@ struct HmpContext {
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
 	int refine_max_leaders = 256;    // per scene (single-scene plans); batches use min(this, 32)
 	int last_n_leaders = 0;
+	HmpEquisampled equi{};           // second generator of the pool (hmp_set_equisampled); enabled = 0 after hmp_create
+	std::vector<double> last_equi;   // its velocity samples of the last plan ([n][3])
 	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
 	int dilated_scenes = 0;
 	int prune_obstacle = 1;          // HMP_NO_PRUNE=1 in the environment disables the dilated-map pruning (A/B timing)
@@ -164,7 +166,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -272,7 +274,9 @@ int build_dev_params(const HmpContext* ctx, const HmpSampling* sampling, int n_e
 		}
 	}
 	D.n_grid = (int)total;
-	D.n_candidates = (int)total + n_extra;
+	D.n_social = (int)total + n_extra;
+	D.n_equi = 0;
+	D.n_candidates = D.n_social;
 
 	D.size_x = ctx->size_x;
 	D.size_y = ctx->size_y;
@@ -478,8 +482,71 @@ void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev,
 	}
 }
 
-struct CtrlLayout {  // d_ctrl: counters [n][4] u32 | hv_out [n][4] u32 | best_out [n][2] f64
-	size_t off_counters, off_hv, off_best, total;
+// Velocity samples of the equisampled generator for one cycle: src/humap_planner.cpp:1317-1361 (min_vel_x rule) +
+// base_local_planner::SimpleTrajectoryGenerator::initialise / VelocityIterator [RECALLED]. Eigen::Vector3f state: float stores.
+void velocity_iterator(double vmin, double vmax, int num_samples, std::vector<double>& out) {
+	out.clear();
+	if (vmin == vmax) {
+		out.push_back(vmin);
+		return;
+	}
+	num_samples = std::max(2, num_samples);
+	const double step = (vmax - vmin) / double(std::max(1, num_samples - 1));
+	double next = vmin;
+	for (int j = 0; j < num_samples - 1; ++j) {
+		const double current = next;
+		next += step;
+		out.push_back(current);
+		if (current < 0 && next > 0) out.push_back(0.0);
+	}
+	out.push_back(vmax);
+}
+
+void equisampled_samples(const HmpParams& P, const HmpWorld& w, const HmpEquisampled& eq, DevParams& D, std::vector<double>& samples) {
+	samples.clear();
+	const HmpLimits& L = P.limits;
+	const double sim_time = P.general.sim_time, sim_period = P.general.sim_period;
+	const double from_min = std::max(std::max(eq.min_vel_x, L.min_vel_x), std::max(eq.min_vel_x, w.vel_x - L.acc_lim_x * sim_period));
+	const double min_vel_x = std::min(from_min, L.max_vel_x);
+	double max_vel_x = L.max_vel_x, max_vel_y = L.max_vel_y;
+	const double min_vel_y = L.min_vel_y, max_vel_th = L.max_vel_theta, min_vel_th = -L.max_vel_theta;
+	const float pos[3] = {(float)w.robot_x, (float)w.robot_y, (float)w.robot_yaw};
+	const float vel[3] = {(float)w.vel_x, (float)w.vel_y, (float)w.vel_th};
+	const float acc[3] = {(float)L.acc_lim_x, (float)L.acc_lim_y, (float)L.acc_lim_theta};
+	for (int k = 0; k < 3; ++k) {
+		D.equi_pos[k] = pos[k];
+		D.equi_vel[k] = vel[k];
+		D.equi_acc[k] = acc[k];
+	}
+	D.equi_continued = eq.continued_acceleration ? 1 : 0;
+	const float vs[3] = {(float)eq.vx_samples, (float)eq.vy_samples, (float)eq.vth_samples};
+	if (!(vs[0] * vs[1] * vs[2] > 0)) return;
+	const double window = eq.continued_acceleration ? sim_time : sim_period;   // use_dwa = !continued_acceleration
+	if (eq.continued_acceleration) {
+		const float gx = (float)w.goal_x, gy = (float)w.goal_y;
+		const double dist = std::hypot(gx - pos[0], gy - pos[1]);
+		max_vel_x = std::max(std::min(max_vel_x, dist / sim_time), min_vel_x);
+		max_vel_y = std::max(std::min(max_vel_y, dist / sim_time), min_vel_y);
+	}
+	const float hi[3] = {(float)std::min(max_vel_x, vel[0] + acc[0] * window), (float)std::min(max_vel_y, vel[1] + acc[1] * window),
+	                     (float)std::min(max_vel_th, vel[2] + acc[2] * window)};
+	const float lo[3] = {(float)std::max(min_vel_x, vel[0] - acc[0] * window), (float)std::max(min_vel_y, vel[1] - acc[1] * window),
+	                     (float)std::max(min_vel_th, vel[2] - acc[2] * window)};
+	std::vector<double> xs, ys, ts;
+	velocity_iterator(lo[0], hi[0], (int)vs[0], xs);
+	velocity_iterator(lo[1], hi[1], (int)vs[1], ys);
+	velocity_iterator(lo[2], hi[2], (int)vs[2], ts);
+	for (double vx : xs)
+		for (double vy : ys)
+			for (double vt : ts) {
+				samples.push_back((double)(float)vx);
+				samples.push_back((double)(float)vy);
+				samples.push_back((double)(float)vt);
+			}
+}
+
+struct CtrlLayout {  // d_ctrl: counters [n][4] u32 | hv_out [n][4] u32 | best_out [n][2] f64 | best of the equisampled sweep [n][2] f64
+	size_t off_counters, off_hv, off_best, off_best2, total;
 };
 CtrlLayout ctrl_layout(int n_scenes) {
 	CtrlLayout c;
@@ -487,7 +554,8 @@ CtrlLayout ctrl_layout(int n_scenes) {
 	c.off_hv = (size_t)n_scenes * 4 * sizeof(unsigned int);
 	c.off_best = c.off_hv + (size_t)n_scenes * 4 * sizeof(unsigned int);
 	c.off_best = (c.off_best + 15) / 16 * 16;
-	c.total = c.off_best + (size_t)n_scenes * 2 * sizeof(double);
+	c.off_best2 = c.off_best + (size_t)n_scenes * 2 * sizeof(double);
+	c.total = c.off_best2 + (size_t)n_scenes * 2 * sizeof(double);
 	return c;
 }
 
@@ -517,7 +585,7 @@ struct PlanLaunch {
 
 int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* blocks_x_out, size_t* smem_out,
                 int* costmap_in_smem_out) {
-	const int C = D.n_candidates;
+	const int C = D.n_social;
 	size_t cm_bytes = (size_t)ctx->costmap_stride;
 	int in_smem = 1;
 	size_t smem = hmp_dev_smem_bytes(pl.scene_stride, (uint32_t)cm_bytes, 1);
@@ -611,7 +679,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	ctx->h_out.release();
@@ -876,7 +944,8 @@ static int validate_world(const HmpWorld* w) {
 
 // Runs the selection kernel + the winner's detail pass for scenes already resident on the device.
 static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<double>& amp_table, const HmpSample* extra,
-                     int n_extra, const PlanLaunch& pl, HmpResult* results, double* poses_out, int32_t poses_capacity) {
+                     int n_extra, const std::vector<double>& equi, const PlanLaunch& pl, HmpResult* results, double* poses_out,
+                     int32_t poses_capacity) {
 	const int C = D.n_candidates;
 	const int T = D.T;
 	const int NS = pl.n_scenes;
@@ -884,6 +953,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	if ((rc = ctx->d_params.ensure(sizeof(DevParams)))) return rc;
 	if ((rc = ctx->d_amp.ensure(amp_table.size() * sizeof(double)))) return rc;
 	if ((rc = ctx->d_extra.ensure(std::max<size_t>(1, (size_t)n_extra) * sizeof(HmpSample)))) return rc;
+	if ((rc = ctx->d_equi.ensure(std::max<size_t>(1, equi.size()) * sizeof(double)))) return rc;
 	if ((rc = ctx->d_totals.ensure((size_t)NS * C * sizeof(double)))) return rc;
 	const CtrlLayout cl = ctrl_layout(NS);
 	if ((rc = ctx->d_ctrl.ensure(cl.total))) return rc;
@@ -902,6 +972,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	CU(cudaMemcpyAsync(ctx->d_params.p, &D, sizeof(DevParams), cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ctx->d_amp.p, amp_table.data(), amp_table.size() * sizeof(double), cudaMemcpyHostToDevice, st));
 	if (n_extra > 0) CU(cudaMemcpyAsync(ctx->d_extra.p, extra, (size_t)n_extra * sizeof(HmpSample), cudaMemcpyHostToDevice, st));
+	if (!equi.empty()) CU(cudaMemcpyAsync(ctx->d_equi.p, equi.data(), equi.size() * sizeof(double), cudaMemcpyHostToDevice, st));
 	CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, cl.total, st));
 
 	unsigned char* ctrl = (unsigned char*)ctx->d_ctrl.p;
@@ -910,6 +981,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.params = (const DevParams*)ctx->d_params.p;
 	A.amp_values = (const double*)ctx->d_amp.p;
 	A.extra_samples = (const double*)ctx->d_extra.p;
+	A.equi_samples = (const double*)ctx->d_equi.p;
 	A.scenes = (const uint8_t*)ctx->d_scenes.p;
 	A.scene_stride = pl.scene_stride;
 	A.n_scenes = NS;
@@ -918,7 +990,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.costmap_in_smem = in_smem;
 	A.precise = (ctx->precise == 1) ? 1 : 0;
 	A.mapgrids = (const float*)ctx->d_mapgrids.p;
-	A.n_work = C;
+	A.n_work = D.n_social;
 	A.totals = (double*)ctx->d_totals.p;
 	A.block_best = (unsigned long long*)ctx->d_block_best.p;
 	A.counters = (unsigned int*)(ctrl + cl.off_counters);
@@ -943,6 +1015,17 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			ctx->dilated_scenes = NS;
 		}
 		A.dilated = (const uint8_t*)ctx->d_dilated.p;
+	}
+	if (D.n_equi > 0) {
+		// the second generator of the pool first (a few dozen kinematic rollouts): its best is merged by the main sweep's last block
+		KernelArgs E = A;
+		E.n_work = D.n_equi;
+		E.cand_offset = D.n_social;
+		E.best_out = (double*)(ctrl + cl.off_best2);
+		CU(hmp_dev_launch_plan(&E, (D.n_equi + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 2, smem, st));
+		ctx->launches++;
+		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
+		A.best_init = E.best_out;
 	}
 	CU(hmp_dev_launch_plan(&A, blocks_x, 0, smem, st));
 	ctx->launches++;
@@ -1031,6 +1114,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		r.best_index = best;
 		r.status = best >= 0 ? 0 : 1;
 		r.n_candidates = C;
+		r.n_social = D.n_social;
 		r.n_generated = (int)h_counters[4 * s + 2];
 		r.n_valid = (int)h_counters[4 * s + 3];
 		r.best_total = best >= 0 ? h_best[2 * s] : -7.0;  // caller pre-sets cost_ = -7, humap_planner.cpp:1364
@@ -1056,8 +1140,10 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 					r.amplifiers[a] = amp_table[(size_t)a * HMP_MAX_AMP_VALUES + rem % n];
 					rem /= n;
 				}
-			} else if (extra) {
+			} else if (best < D.n_social && extra) {
 				for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) r.amplifiers[a] = extra[best - D.n_grid].amp[a];
+			} else {
+				for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) r.amplifiers[a] = std::numeric_limits<double>::quiet_NaN();
 			}
 			if (poses_out && s == 0) {
 				int n = std::min<int>(r.n_poses, poses_capacity);
@@ -1072,6 +1158,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	ctx->last_dev_params = D;
 	if (&amp_table != &ctx->last_amp_table) ctx->last_amp_table = amp_table;
 	if (extra != ctx->last_extra.data()) ctx->last_extra.assign(extra, extra + n_extra);
+	if (&equi != &ctx->last_equi) ctx->last_equi = equi;
 	ctx->last_valid = true;
 	return HMP_OK;
 }
@@ -1114,8 +1201,14 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 	pack_scene(ctx, *world, ctx->hv_prev, D.dt_d, (unsigned char*)ctx->h_stage.p);
 	uint32_t used = reinterpret_cast<DevScene*>(ctx->h_stage.p)->blob_bytes;
 	CU(cudaMemcpyAsync(ctx->d_scenes.p, ctx->h_stage.p, used, cudaMemcpyHostToDevice, ctx->stream));
+	std::vector<double> equi;
+	if (ctx->equi.enabled) {
+		equisampled_samples(ctx->params, *world, ctx->equi, D, equi);
+		D.n_equi = (int)(equi.size() / 3);
+		D.n_candidates = D.n_social + D.n_equi;
+	}
 	PlanLaunch pl{1, used, n_extra, T};
-	return run_cycle(ctx, D, amp_table, extra, n_extra, pl, result, poses_out, poses_capacity);
+	return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
 }
 
 int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, const uint8_t* cells,
@@ -1194,7 +1287,7 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		for (bool& b : ctx->have_grid) b = true;
 	}
 	PlanLaunch pl{n_scenes, (uint32_t)stride, 0, T};
-	return run_cycle(ctx, D, amp_table, nullptr, 0, pl, results, nullptr, 0);
+	return run_cycle(ctx, D, amp_table, nullptr, 0, std::vector<double>(), pl, results, nullptr, 0);
 }
 
 // Re-runs the selection of the last plan on the data still resident on the device (no host<->device
@@ -1207,7 +1300,7 @@ int hmp_replan_resident(HmpContext* ctx, HmpResult* results) {
 	CU(cudaSetDevice(ctx->device));
 	PlanLaunch pl{ctx->last_n_scenes, ctx->last_scene_stride, (int)ctx->last_extra.size(), ctx->last_T};
 	return run_cycle(ctx, ctx->last_dev_params, ctx->last_amp_table, pl.n_extra ? ctx->last_extra.data() : nullptr, pl.n_extra,
-	                 pl, results, nullptr, 0);
+	                 ctx->last_equi, pl, results, nullptr, 0);
 }
 
 int hmp_get_explored_totals(HmpContext* ctx, double* totals, int32_t n) {
@@ -1260,6 +1353,7 @@ int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n, do
 	A.params = (const DevParams*)ctx->d_params.p;
 	A.amp_values = (const double*)ctx->d_amp.p;
 	A.extra_samples = (const double*)ctx->d_extra.p;
+	A.equi_samples = (const double*)ctx->d_equi.p;
 	A.scenes = (const uint8_t*)ctx->d_scenes.p;
 	A.scene_stride = ctx->last_scene_stride;
 	A.n_scenes = 1;
@@ -1407,6 +1501,22 @@ int hmp_set_precision(HmpContext* ctx, int32_t fp64) {
 		return HMP_E_INVALID;
 	}
 	ctx->precise = (fp64 == 2) ? 2 : (fp64 ? 1 : 0);
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq) {
+	if (!ctx) {
+		set_err("null context");
+		return HMP_E_INVALID;
+	}
+	if (eq && eq->enabled && (eq->vx_samples < 0 || eq->vy_samples < 0 || eq->vth_samples < 0 ||
+	                          (long long)(eq->vx_samples + 1) * (eq->vy_samples + 1) * (eq->vth_samples + 1) > (1 << 20))) {
+		set_err("bad equisampled sample counts");
+		return HMP_E_INVALID;
+	}
+	if (eq) ctx->equi = *eq;
+	else ctx->equi.enabled = 0;
 	ctx->last_valid = false;
 	return HMP_OK;
 }

@@ -120,7 +120,13 @@ struct alignas(16) DevParams {
 	/* --- candidates */
 	int32_t amp_n[HMP_NUM_AMPLIFIERS];
 	int32_t n_grid;               /* product of amp_n                                  */
-	int32_t n_candidates;         /* n_grid + n_extra                                  */
+	int32_t n_candidates;         /* n_social + n_equi                                 */
+	int32_t n_social;             /* n_grid + n_extra: candidates of the social generator */
+	int32_t n_equi;               /* equisampled-velocity candidates appended after them (SimpleTrajectoryGenerator) */
+	int32_t equi_continued;       /* continued_acceleration_                           */
+	int32_t _pade;
+	float equi_pos[3], equi_vel[3], equi_acc[3];   /* Eigen::Vector3f pos_, vel_, getAccLimits() of the generator */
+	float _padq[3];
 	/* --- costmap geometry */
 	int32_t size_x, size_y;
 	double origin_x, origin_y, resolution, inv_resolution;
@@ -150,6 +156,7 @@ struct KernelArgs {
 	const DevParams* params;         /* device */
 	const double* amp_values;        /* [10][HMP_MAX_AMP_VALUES] device                           */
 	const double* extra_samples;     /* [n_extra][10] device, or null                             */
+	const double* equi_samples;      /* [n_equi][3] target velocities (float values), or null      */
 	const uint8_t* scenes;           /* n_scenes blobs, stride scene_stride bytes                  */
 	uint32_t scene_stride;
 	int32_t n_scenes;
@@ -177,6 +184,10 @@ struct KernelArgs {
 	const uint8_t* dilated;          /* [n_scenes] maps, stride costmap_stride: max costmap cost over the disc that contains every
 	                                    cell the footprint critic can touch from a centre in that cell (255 outside the map), or
 	                                    null: lets the obstacle critic skip poses that cannot raise its running maximum        */
+	int32_t cand_offset;             /* sweep launches: candidate = work index + cand_offset (the equisampled sweep starts at n_social) */
+	int32_t _pado;
+	const double* best_init;         /* [n_scenes][2] (total, index) of an earlier sweep over other candidates of the same pool, merged
+	                                    into best_out by the last block (ties: lower index wins), or null                */
 	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
 	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
 	int32_t _padt;

@@ -236,6 +236,19 @@ typedef struct HmpSample {
 	double amp[HMP_NUM_AMPLIFIERS];
 } HmpSample;
 
+/* The second generator of HumapPlanner's pool: base_local_planner::SimpleTrajectoryGenerator fed with equisampled
+ * velocities (TrajectoryGeneration, humap_config.h:154-174; wiring src/humap_planner.cpp:196-203, :1317-1361). Its
+ * candidates are appended after the social ones (generator_list order, humap_planner.cpp:85-88) and compete in the
+ * same selection. Candidate index: [0, n_social) social grid + extra samples, [n_social, n_candidates) equisampled,
+ * in the generator's own order (vx outermost, vth innermost). */
+typedef struct HmpEquisampled {
+	int32_t enabled;                 /* use_equisampled_velocities_generator                                     */
+	int32_t vx_samples, vy_samples, vth_samples;   /* equisampled_vx / vy / vth                                   */
+	double min_vel_x;                /* equisampled_min_vel_x                                                    */
+	int32_t continued_acceleration;  /* equisampled_continued_acceleration (setParameters gets use_dwa = !this)   */
+	int32_t _pad;
+} HmpEquisampled;
+
 /* ---- result ------------------------------------------------------------------------------- */
 typedef struct HmpResult {
 	int32_t status;                /* 0: a valid trajectory was found; 1: none valid (cost < 0)   */
@@ -252,6 +265,9 @@ typedef struct HmpResult {
 	double highest_valid_cost[HMP_NUM_MAPGRIDS];  /* highest_valid_cost_ after the cycle (map_grid_cost_function.cpp:87,135) */
 	double gpu_ms;                 /* device time of the cycle (CUDA events on the launching stream), milliseconds */
 	double gpu_ms_select;          /* ... of the rollout + scoring + selection kernel alone                        */
+	int32_t n_social;              /* candidates of the social generator (grid + extra); best_index >= n_social means the
+	                                  winner came from the equisampled generator (amplifiers are NaN then)          */
+	int32_t _pad;
 } HmpResult;
 
 typedef struct HmpContext HmpContext;
@@ -303,6 +319,11 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 /* Reads a MapGrid slot back (row-major doubles); diagnostics / parity tests. */
 int hmp_get_mapgrid(HmpContext* ctx, int32_t grid, double* target_dist_out);
 
+/* Replaces generator_vel_space_.setParameters (humap_planner.cpp:196-203) + the per-cycle initialise (:1317-1361) of the
+ * equisampled generator for the following hmp_plan calls (single-scene plans; NULL or enabled = 0 turns it off, which
+ * is the state after hmp_create). The velocity window is derived per cycle from HmpLimits, HmpGeneral (sim_time,
+ * sim_period), the robot velocity and the goal of the HmpWorld, as the reference does. */
+int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq);
 /* Replaces ObstacleSeparationCostFunction::setFootprint (humap_planner.cpp:1059); xy interleaved. */
 int hmp_set_footprint(HmpContext* ctx, const double* xy, int32_t n_points);
 

@@ -29,6 +29,7 @@
 #include <limits>
 #include <queue>
 #include <string>
+#include <array>
 #include <vector>
 
 namespace {
@@ -1671,6 +1672,152 @@ bool areVelocityLimitsFulfilled(const HmpLimits& l, double speed_linear, double 
 	return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Equisampled velocities: base_local_planner::SimpleTrajectoryGenerator + VelocityIterator [RECALLED from upstream
+// ros-planning/navigation, parity unpinned] as wired by src/humap_planner.cpp:196-203 and :1317-1361 (first-party).
+// The upstream generator works on Eigen::Vector3f: positions, velocities and acceleration limits are FP32 values,
+// the expressions between them are evaluated in double (cos/sin/hypot take double, dt is double) and rounded to
+// float on every store. Restated with the same store points.
+// ------------------------------------------------------------------------------------------------
+// base_local_planner/velocity_iterator.h
+std::vector<double> velocityIteratorSamples(double vmin, double vmax, int num_samples) {
+	std::vector<double> samples;
+	if (vmin == vmax) {
+		samples.push_back(vmin);
+	} else {
+		num_samples = std::max(2, num_samples);
+		double step_size = (vmax - vmin) / double(std::max(1, (num_samples - 1)));
+		double current;
+		double next = vmin;
+		for (int j = 0; j < num_samples - 1; ++j) {
+			current = next;
+			next += step_size;
+			samples.push_back(current);
+			if ((current < 0) && (next > 0)) samples.push_back(0.0);   // a zero between the negative and positive samples
+		}
+		samples.push_back(vmax);
+	}
+	return samples;
+}
+
+struct EquiGenerator {
+	float pos[3], vel[3], acc[3];
+	double sim_time = 0, sim_granularity = 0, angular_sim_granularity = 0, sim_period = 0;
+	bool continued_acceleration = true, discretize_by_time = true;
+	double min_vel_trans = 0, max_vel_trans = 0, min_vel_theta = 0;
+	std::vector<std::array<float, 3>> samples;
+
+	// humap_planner.cpp:1317-1361 + SimpleTrajectoryGenerator::initialise
+	void initialise(const HmpParams& P, const HmpWorld& w, const HmpEquisampled& eq) {
+		const HmpLimits& L = P.limits;
+		sim_time = P.general.sim_time;
+		sim_granularity = P.general.sim_granularity;
+		angular_sim_granularity = P.general.angular_sim_granularity;
+		sim_period = P.general.sim_period;
+		continued_acceleration = eq.continued_acceleration != 0;   // setParameters(..., use_dwa = !continued, ...)
+		const bool use_dwa = !continued_acceleration;
+		discretize_by_time = true;                                  // the `true` of humap_planner.cpp:1360
+		min_vel_trans = L.min_vel_trans;
+		max_vel_trans = L.max_vel_trans;
+		min_vel_theta = L.min_vel_theta;
+		// :1335-1351 (first-party): keep min_vel_x as high as kinematics allow, but not above max_vel_x
+		double maximum_from_min_vel_x = std::max(std::max(eq.min_vel_x, L.min_vel_x),
+		                                         std::max(eq.min_vel_x, w.vel_x - L.acc_lim_x * P.general.sim_period));
+		double min_vel_x = std::min(maximum_from_min_vel_x, L.max_vel_x);
+		double max_vel_x = L.max_vel_x, min_vel_y = L.min_vel_y, max_vel_y = L.max_vel_y;
+		double max_vel_th = L.max_vel_theta, min_vel_th = -1.0 * max_vel_th;
+		pos[0] = (float)w.robot_x; pos[1] = (float)w.robot_y; pos[2] = (float)w.robot_yaw;   // Pose::getAsEigen2D
+		vel[0] = (float)w.vel_x; vel[1] = (float)w.vel_y; vel[2] = (float)w.vel_th;          // Vector::getAsEigen<Vector3f>
+		acc[0] = (float)L.acc_lim_x; acc[1] = (float)L.acc_lim_y; acc[2] = (float)L.acc_lim_theta;   // getAccLimits()
+		const float goal[2] = {(float)w.goal_x, (float)w.goal_y};
+		samples.clear();
+		const float vs[3] = {(float)eq.vx_samples, (float)eq.vy_samples, (float)eq.vth_samples};
+		if (!(vs[0] * vs[1] * vs[2] > 0)) return;
+		float max_vel[3] = {0, 0, 0}, min_vel[3] = {0, 0, 0};
+		if (!use_dwa) {
+			double dist = std::hypot(goal[0] - pos[0], goal[1] - pos[1]);
+			max_vel_x = std::max(std::min(max_vel_x, dist / sim_time), min_vel_x);
+			max_vel_y = std::max(std::min(max_vel_y, dist / sim_time), min_vel_y);
+			max_vel[0] = (float)std::min(max_vel_x, vel[0] + acc[0] * sim_time);
+			max_vel[1] = (float)std::min(max_vel_y, vel[1] + acc[1] * sim_time);
+			max_vel[2] = (float)std::min(max_vel_th, vel[2] + acc[2] * sim_time);
+			min_vel[0] = (float)std::max(min_vel_x, vel[0] - acc[0] * sim_time);
+			min_vel[1] = (float)std::max(min_vel_y, vel[1] - acc[1] * sim_time);
+			min_vel[2] = (float)std::max(min_vel_th, vel[2] - acc[2] * sim_time);
+		} else {
+			max_vel[0] = (float)std::min(max_vel_x, vel[0] + acc[0] * sim_period);
+			max_vel[1] = (float)std::min(max_vel_y, vel[1] + acc[1] * sim_period);
+			max_vel[2] = (float)std::min(max_vel_th, vel[2] + acc[2] * sim_period);
+			min_vel[0] = (float)std::max(min_vel_x, vel[0] - acc[0] * sim_period);
+			min_vel[1] = (float)std::max(min_vel_y, vel[1] - acc[1] * sim_period);
+			min_vel[2] = (float)std::max(min_vel_th, vel[2] - acc[2] * sim_period);
+		}
+		auto xs = velocityIteratorSamples(min_vel[0], max_vel[0], (int)vs[0]);
+		auto ys = velocityIteratorSamples(min_vel[1], max_vel[1], (int)vs[1]);
+		auto ts = velocityIteratorSamples(min_vel[2], max_vel[2], (int)vs[2]);
+		for (double vx : xs)
+			for (double vy : ys)
+				for (double vt : ts) samples.push_back({(float)vx, (float)vy, (float)vt});
+	}
+
+	static void computeNewVelocities(const float target[3], const float v[3], const float a[3], double dt, float out[3]) {
+		for (int i = 0; i < 3; ++i) {
+			if (v[i] < target[i]) out[i] = (float)std::min(double(target[i]), v[i] + a[i] * dt);
+			else out[i] = (float)std::max(double(target[i]), v[i] - a[i] * dt);
+		}
+	}
+
+	// SimpleTrajectoryGenerator::generateTrajectory
+	bool generate(size_t k, BlpTrajectory& traj) const {
+		const float* target = samples[k].data();
+		double vmag = std::hypot(target[0], target[1]);
+		const double eps = 1e-4;
+		traj.cost = -1.0;
+		traj.x.clear();
+		traj.y.clear();
+		traj.th.clear();
+		if ((min_vel_trans >= 0 && vmag + eps < min_vel_trans) && (min_vel_theta >= 0 && std::fabs(target[2]) + eps < min_vel_theta)) return false;
+		if (max_vel_trans >= 0 && vmag - eps > max_vel_trans) return false;
+		int num_steps;
+		if (discretize_by_time) {
+			num_steps = std::ceil(sim_time / sim_granularity);
+		} else {
+			double sim_time_distance = vmag * sim_time;
+			double sim_time_angle = std::fabs(target[2]) * sim_time;
+			num_steps = std::ceil(std::max(sim_time_distance / sim_granularity, sim_time_angle / angular_sim_granularity));
+		}
+		if (num_steps == 0) return false;
+		double dt = sim_time / num_steps;
+		traj.time_delta = dt;
+		float loop_vel[3];
+		if (continued_acceleration) {
+			computeNewVelocities(target, vel, acc, dt, loop_vel);
+		} else {
+			loop_vel[0] = target[0]; loop_vel[1] = target[1]; loop_vel[2] = target[2];
+		}
+		traj.xv = loop_vel[0];
+		traj.yv = loop_vel[1];
+		traj.thetav = loop_vel[2];
+		float p[3] = {pos[0], pos[1], pos[2]};
+		for (int i = 0; i < num_steps; ++i) {
+			traj.x.push_back(p[0]);
+			traj.y.push_back(p[1]);
+			traj.th.push_back(p[2]);
+			if (continued_acceleration) {
+				float nv[3];
+				computeNewVelocities(target, loop_vel, acc, dt, nv);
+				loop_vel[0] = nv[0]; loop_vel[1] = nv[1]; loop_vel[2] = nv[2];
+			}
+			// computeNewPositions
+			float np0 = (float)(p[0] + (loop_vel[0] * std::cos((double)p[2]) + loop_vel[1] * std::cos(M_PI_2 + p[2])) * dt);
+			float np1 = (float)(p[1] + (loop_vel[0] * std::sin((double)p[2]) + loop_vel[1] * std::sin(M_PI_2 + p[2])) * dt);
+			float np2 = (float)(p[2] + loop_vel[2] * dt);
+			p[0] = np0; p[1] = np1; p[2] = np2;
+		}
+		return true;
+	}
+};
+
 struct StepForces {
 	V3 internal, dynamic, stat, human;
 };
@@ -1804,6 +1951,17 @@ int orc_num_candidates(const HmpSampling* sampling, int n_extra) {
 	return (int)(total + n_extra);
 }
 
+int orc_equisampled_samples(const HmpParams* P, const HmpWorld* w, const HmpEquisampled* eq, double* out, int cap) {
+	EquiGenerator g;
+	if (eq && eq->enabled) g.initialise(*P, *w, *eq);
+	for (size_t i = 0; i < g.samples.size() && (int)i < cap; ++i) {
+		out[3 * i] = g.samples[i][0];
+		out[3 * i + 1] = g.samples[i][1];
+		out[3 * i + 2] = g.samples[i][2];
+	}
+	return (int)g.samples.size();
+}
+
 int orc_num_steps(const HmpParams* P, const HmpWorld* w) {
 	return computeStepsNumber(P->general, std::hypot(w->vel_x, w->vel_y), w->vel_th);
 }
@@ -1840,7 +1998,10 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	st.footprint.assign(in->footprint_xy, in->footprint_xy + 2 * in->n_footprint);
 	buildScene(st, *in->params, *in->world);
 	auto samples = buildSamples(*in->sampling, in->extra, in->n_extra);
-	const int C = (int)samples.size();
+	const int n_social = (int)samples.size();
+	EquiGenerator equi;
+	if (in->equisampled && in->equisampled->enabled) equi.initialise(*in->params, *in->world, *in->equisampled);
+	const int C = n_social + (int)equi.samples.size();   // pool order: social generator, then the equisampled one
 	const int c_begin = std::max(0, in->cand_begin);
 	const int c_end = (in->cand_end <= 0) ? C : std::min(C, in->cand_end);
 	FisEngine fis;
@@ -1853,8 +2014,9 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	int n_generated = 0, n_valid = 0;
 	BlpTrajectory traj;
 	for (int ci = c_begin; ci < c_end; ++ci) {
-		double* forces = (out->forces && ci == out->forces_candidate) ? out->forces : nullptr;
-		bool ok = generateTrajectory(*in->params, fis, st.world, st.vel_local, samples[ci], traj, forces);
+		double* forces = (out->forces && ci == out->forces_candidate && ci < n_social) ? out->forces : nullptr;
+		bool ok = (ci < n_social) ? generateTrajectory(*in->params, fis, st.world, st.vel_local, samples[ci], traj, forces)
+		                          : equi.generate((size_t)(ci - n_social), traj);
 		if (out->generated) out->generated[ci] = ok ? 1 : 0;
 		if (out->n_poses) out->n_poses[ci] = (int)traj.size();
 		if (out->poses) {
@@ -1895,6 +2057,7 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	HmpResult& r = out->result;
 	std::memset(&r, 0, sizeof(r));
 	r.n_candidates = C;
+	r.n_social = n_social;
 	r.n_generated = n_generated;
 	r.n_valid = n_valid;
 	r.best_index = best_idx;
@@ -1908,7 +2071,8 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 		r.yv = best_traj.yv;
 		r.thetav = best_traj.thetav;
 		r.n_poses = (int)best_traj.size();
-		for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) r.amplifiers[a] = samples[best_idx].amp[a];
+		for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a)
+			r.amplifiers[a] = (best_idx < n_social) ? samples[best_idx].amp[a] : std::numeric_limits<double>::quiet_NaN();
 		if (out->best_poses) {
 			for (size_t i = 0; i < best_traj.size(); ++i) {
 				out->best_poses[3 * i] = best_traj.x[i];

@@ -33,6 +33,8 @@ typedef struct OrcPlanInput {
 	/* candidate sub-range [cand_begin, cand_end) to evaluate; cand_end <= 0 means all (used by the
 	 * multi-threaded CPU baseline) */
 	int32_t cand_begin, cand_end;
+	/* second generator of the pool (may be NULL): equisampled velocities, appended after the social candidates */
+	const HmpEquisampled* equisampled;
 } OrcPlanInput;
 
 typedef struct OrcPlanOutput {
@@ -54,6 +56,8 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out);
 int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, const double seed[3], double* raw_costs,
                          double* total, double* hv_out);
 int orc_num_candidates(const HmpSampling* sampling, int n_extra);
+/* velocity samples of the equisampled generator for this cycle: out[n][3] floats stored as doubles; returns n */
+int orc_equisampled_samples(const HmpParams* P, const HmpWorld* w, const HmpEquisampled* eq, double* out, int cap);
 int orc_num_steps(const HmpParams* P, const HmpWorld* w);
 int orc_samples(const HmpSampling* sampling, const HmpSample* extra, int n_extra, HmpSample* out);
 void orc_mapgrid_compute(const uint8_t* cells, int size_x, int size_y, double origin_x, double origin_y,

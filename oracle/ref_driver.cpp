@@ -326,6 +326,7 @@ int ref_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	HmpResult& r = out->result;
 	std::memset(&r, 0, sizeof(r));
 	r.n_candidates = Cn;
+	r.n_social = Cn;   // the second generator of the pool is third-party code (base_local_planner): not part of this build
 	r.n_generated = n_generated;
 	r.n_valid = n_valid;
 	r.best_index = best_idx;

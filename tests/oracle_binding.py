@@ -8,8 +8,8 @@ import subprocess
 
 import numpy as np
 
-from humap_local_planner_b200.capi import (HmpParams, HmpWorld, HmpSampling, HmpSample, HmpResult, NUM_COSTS,
-                                           NUM_MAPGRIDS, NUM_AMPLIFIERS, Scene)
+from humap_local_planner_b200.capi import (HmpParams, HmpWorld, HmpSampling, HmpSample, HmpResult, HmpEquisampled,
+                                           NUM_COSTS, NUM_MAPGRIDS, NUM_AMPLIFIERS, Scene)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = os.path.join(ROOT, "oracle", "_build", "libhmp_oracle.so")
@@ -28,6 +28,7 @@ class OrcPlanInput(C.Structure):
         ("target_dist", C.c_void_p * NUM_MAPGRIDS), ("highest_valid_cost_prev", _d * NUM_MAPGRIDS),
         ("footprint_xy", C.c_void_p), ("n_footprint", _i),
         ("early_exit", _i), ("cand_begin", _i), ("cand_end", _i),
+        ("equisampled", C.c_void_p),
     ]
 
 
@@ -74,7 +75,7 @@ def ref_lib() -> C.CDLL:
     global _ref_lib
     if _ref_lib is None:
         lib()  # libhmp_oracle.so first: the stand-ins' orc_tp_* hooks resolve against it
-        if not os.path.exists(_REF_LIB):
+        if os.path.isdir("/root/reference/src"):   # incremental; on the GPU box the prebuilt library is used as is
             subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
         _ref_lib = C.CDLL(_REF_LIB)
         _ref_lib.ref_plan.argtypes = [C.POINTER(OrcPlanInput), C.POINTER(OrcPlanOutput)]
@@ -93,12 +94,27 @@ def num_candidates(sampling: HmpSampling, n_extra: int = 0) -> int:
     return lib().orc_num_candidates(C.byref(sampling), n_extra)
 
 
+def equisampled_samples(params: HmpParams, world: HmpWorld, eq: HmpEquisampled) -> np.ndarray:
+    """Velocity samples (vx, vy, vth) of the equisampled generator for this cycle, in generator order."""
+    L = lib()
+    L.orc_equisampled_samples.argtypes = [C.POINTER(HmpParams), C.POINTER(HmpWorld), C.POINTER(HmpEquisampled), C.c_void_p, C.c_int]
+    n = L.orc_equisampled_samples(C.byref(params), C.byref(world), C.byref(eq), None, 0)
+    out = np.zeros((max(n, 1), 3))
+    L.orc_equisampled_samples(C.byref(params), C.byref(world), C.byref(eq), _p(out), n)
+    return out[:n]
+
+
+def num_equisampled(params: HmpParams, world: HmpWorld, eq: HmpEquisampled) -> int:
+    return equisampled_samples(params, world, eq).shape[0]
+
+
 def num_steps(params: HmpParams, world: HmpWorld) -> int:
     return lib().orc_num_steps(C.byref(params), C.byref(world))
 
 
-def _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range):
+def _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range, equisampled=None):
     inp = OrcPlanInput()
+    inp.equisampled = C.addressof(equisampled) if equisampled is not None else None
     inp.params = C.pointer(params)
     inp.world = C.pointer(scene.world)
     inp.sampling = C.pointer(sampling)
@@ -134,7 +150,7 @@ def score_trajectory(params: HmpParams, scene: Scene, sampling: HmpSampling, pos
 
 def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, early_exit: bool = False,
          cand_range=(0, 0), want=("totals", "costs", "seeds", "poses", "n_poses", "generated"), forces_candidate: int = -1,
-         impl: str = "oracle"):
+         impl: str = "oracle", equisampled: HmpEquisampled = None):
     """Runs orc_plan (impl="oracle") or ref_plan (impl="ref": the reference's own sources, oracle/ref_driver.cpp) and
     returns a dict of numpy arrays (+ 'result': HmpResult)."""
     L = lib()
@@ -145,8 +161,10 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
         ex = np.ascontiguousarray(extra, dtype=np.float64).reshape(-1, NUM_AMPLIFIERS)
         n_extra = ex.shape[0]
     Cn = num_candidates(sampling, n_extra)
+    if equisampled is not None and impl == "oracle":
+        Cn += num_equisampled(params, scene.world, equisampled)
     T = num_steps(params, scene.world)
-    inp = _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range)
+    inp = _make_input(params, scene, sampling, ex, n_extra, early_exit, cand_range, equisampled if impl == "oracle" else None)
     out = OrcPlanOutput()
     arrs = {}
     if "totals" in want:
@@ -183,11 +201,11 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     return arrs
 
 
-def plan_sampled(params, scene, sampling, indices):
+def plan_sampled(params, scene, sampling, indices, equisampled=None):
     """Oracle results for an explicit list of candidate indices (one orc_plan call per candidate)."""
     out = {"totals": [], "costs": [], "poses": [], "seeds": [], "n_poses": []}
     for i in indices:
-        r = plan(params, scene, sampling, cand_range=(int(i), int(i) + 1))
+        r = plan(params, scene, sampling, cand_range=(int(i), int(i) + 1), equisampled=equisampled)
         for k in out:
             out[k].append(r[k][int(i)])
     return {k: np.array(v) for k, v in out.items()}

@@ -14,7 +14,7 @@ import pytest
 import golden_cases as gc
 import oracle_binding as ob
 from humap_local_planner_b200 import scenes, config
-from humap_local_planner_b200.capi import COST_NAMES, NUM_COSTS
+from humap_local_planner_b200.capi import COST_NAMES, NUM_COSTS, HmpEquisampled
 
 pytestmark = pytest.mark.gpu
 
@@ -777,3 +777,86 @@ def test_obstacle_pruning_is_exact(planner, name, seed, variant):
     assert np.array_equal(np.array(a[3]), np.array(b[3]), equal_nan=True)
     assert np.array_equal(a[4], b[4])
     assert (a[4] >= 0).sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row 2: the equisampled-velocity generator pooled with the social one on the device
+# ---------------------------------------------------------------------------------------------------------------
+def _equi(vx=5, vy=1, vth=10, min_vel_x=0.1, continued=1):
+    return HmpEquisampled(1, vx, vy, vth, min_vel_x, continued, 0)
+
+
+@pytest.mark.parametrize("seed,base_vel,continued,precise", [(0, (0.3, 0.0, 0.0), 1, 1), (1, (0.3, 0.0, 0.0), 1, 0),
+                                                             (2, (0.9, 0.0, -0.4), 1, 1), (3, (0.0, 0.0, 0.0), 0, 1),
+                                                             (4, (0.6, 0.0, 0.5), 0, 0), (5, (1.2, 0.0, 0.2), 1, 2)])
+def test_equisampled_pool(planner, seed, base_vel, continued, precise):
+    """Both generators in one pool (humap_planner.cpp:85-95): candidate order, every equisampled trajectory and its
+    critics, and the selection over the pooled candidates against the oracle."""
+    cfg = scenes.CONFIGS["cfg0"]
+    sc = scenes.make_scene(cfg, seed, base_vel=base_vel)
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    eq = _equi(continued=continued)
+    planner.set_precision(precise)
+    planner.set_params(params)
+    planner.set_scene(sc)
+    planner.set_equisampled(eq)
+    try:
+        res, poses = planner.plan(sc.world, smp)
+        C, ns = res.n_candidates, res.n_social
+        T = planner.num_steps()
+        o = ob.plan(params, sc, smp, equisampled=eq)
+        assert ns == 72 and C == o["C"] and C - ns == len(ob.equisampled_samples(params, sc.world, eq)) and C - ns >= 50
+        idx = np.arange(ns, C, dtype=np.int32)
+        ex = planner.explain(idx)
+        g = planner.explored_totals(C)
+    finally:
+        planner.set_equisampled(None)
+        planner.set_precision(False)
+    # generator: same rejections, same float poses (bit-identical up to a last-place difference of the device sincos)
+    assert np.array_equal(ex["n_poses"] == T, o["generated"][ns:] == 1)
+    gen = o["generated"][ns:] == 1
+    assert gen.sum() >= 20
+    assert np.abs(ex["poses"][gen] - o["poses"][ns:][gen]).max() < 2e-6
+    assert np.abs(ex["seeds"][gen] - o["seeds"][ns:][gen]).max() < 1e-7
+    # critics on (nearly) identical poses: integer-valued ones exactly (a vertex on a cell edge may flip), others 1e-4
+    gc_, oc = ex["costs"][gen], o["costs"][ns:][gen]
+    assert np.array_equal(np.isnan(gc_), np.isnan(oc))
+    for k in range(NUM_COSTS):
+        m = ~np.isnan(oc[:, k])
+        if not m.any():
+            continue
+        if k <= 4:
+            assert (gc_[m, k] != oc[m, k]).mean() <= 0.05, COST_NAMES[k]
+        else:
+            bad = (_rel_err(gc_[m, k], oc[m, k]) > REL) & (np.abs(gc_[m, k] - oc[m, k]) > 2e-5)
+            assert bad.mean() <= 0.05, (COST_NAMES[k], float(np.abs(gc_[m, k] - oc[m, k]).max()))
+    # totals and codes of the equisampled candidates
+    ge, oe = g[ns:], o["totals"][ns:]
+    assert ((ge < 0) == (oe < 0)).mean() >= 0.95
+    v = (ge >= 0) & (oe >= 0)
+    assert np.median(_rel_err(ge[v], oe[v])) < 1e-5
+    # selection over the pool
+    full = o["totals"]
+    valid = np.where(full >= 0)[0]
+    order = valid[np.argsort(full[valid], kind="stable")]
+    top2_close = len(order) > 1 and (full[order[1]] - full[order[0]]) <= 1e-4 * abs(full[order[0]])
+    assert res.best_index == int(order[0]) or top2_close
+    assert abs(res.best_total - full[res.best_index]) <= 1e-4 * abs(full[res.best_index])
+    if res.best_index >= ns:
+        assert np.all(np.isnan(np.array(res.amplifiers)))
+        assert np.abs(poses - o["poses"][res.best_index]).max() < 2e-6
+
+
+def test_equisampled_off_is_the_default_and_changes_nothing(planner):
+    cfg, sc, params, smp = _setup(planner, "cfg0", 2)
+    r0, _ = planner.plan(sc.world, smp)
+    t0 = planner.explored_totals(r0.n_candidates)
+    planner.set_equisampled(_equi())
+    r1, _ = planner.plan(sc.world, smp)
+    t1 = planner.explored_totals(r1.n_candidates)
+    planner.set_equisampled(None)
+    r2, _ = planner.plan(sc.world, smp)
+    assert r0.n_candidates == r0.n_social == 72 and r1.n_social == 72 and r1.n_candidates > 72 and r2.n_candidates == 72
+    assert np.array_equal(t0, t1[:72]) and r2.best_index == r0.best_index and r2.best_total == r0.best_total
+    assert r1.n_generated >= r0.n_generated and r1.n_valid >= r0.n_valid
