@@ -126,7 +126,7 @@ ABI_SYMBOLS = (
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
-    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled",
+    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -180,6 +180,8 @@ def load_library() -> C.CDLL:
     lib.hmp_set_refinement.restype = C.c_int
     lib.hmp_set_equisampled.argtypes = [C.c_void_p, C.c_void_p]
     lib.hmp_set_equisampled.restype = C.c_int
+    lib.hmp_compute_cost_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hmp_compute_cost_cloud.restype = C.c_int
     lib.hmp_last_num_leaders.argtypes = [C.c_void_p]
     lib.hmp_last_num_leaders.restype = C.c_int
     lib.hmp_launch_count.restype = C.c_int64
@@ -259,12 +261,21 @@ class Planner:
         """Second generator of the pool (equisampled velocities); None turns it off."""
         self._check(self._lib.hmp_set_equisampled(self._ctx, C.byref(eq) if eq is not None else None))
 
+    def cost_cloud(self):
+        """HumapPlanner::computeCellCost for every cell: (cloud [size_y][size_x][6] float32, valid [size_y][size_x] bool)."""
+        n = self._size_y * self._size_x
+        out = np.zeros((n, 6), dtype=np.float32)
+        valid = np.zeros(n, dtype=np.uint8)
+        self._check(self._lib.hmp_compute_cost_cloud(self._ctx, _ptr(out), _ptr(valid)))
+        return out.reshape(self._size_y, self._size_x, 6), valid.reshape(self._size_y, self._size_x).astype(bool)
+
     def last_num_leaders(self) -> int:
         return int(self._lib.hmp_last_num_leaders(self._ctx))
 
     def set_costmap(self, cells: np.ndarray, origin_x: float, origin_y: float, resolution: float):
         cells = np.ascontiguousarray(cells, dtype=np.uint8)
         sy, sx = cells.shape
+        self._size_y, self._size_x = sy, sx
         self._check(self._lib.hmp_set_costmap(self._ctx, _ptr(cells), sx, sy, origin_x, origin_y, resolution))
 
     def set_mapgrid(self, grid: int, target_dist: np.ndarray, hv_prev: float = 0.0):

@@ -47,6 +47,8 @@ extern "C" cudaError_t hmp_dev_launch_wavefront(const uint8_t* cm, int sx, int s
 extern "C" cudaError_t hmp_dev_launch_wavefront_queue(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
                                                       int* status, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_cost_cloud(const DevParams* P, int n_cells, const uint8_t* cm, const float* mapgrids, const double* hv,
+                                                 float* out, uint8_t* valid, cudaStream_t stream);
 
 namespace {
 
@@ -1466,6 +1468,38 @@ int hmp_debug_footprint_cost(HmpContext* ctx, const double* xyt, int32_t n, doub
 	CU(hmp_dev_launch_footprint_cost((const DevParams*)ctx->d_params.p, (const uint8_t*)ctx->d_costmaps.p, dx, n, dc, st));
 	ctx->launches++;
 	CU(cudaMemcpyAsync(cost, dc, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return HMP_OK;
+}
+
+// HumapPlanner::computeCellCost for every cell of the costmap (diagnostics; see cost_cloud_kernel)
+int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!cloud6 || !valid) {
+		set_err("null output");
+		return HMP_E_INVALID;
+	}
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!ctx->have_grid[g]) {
+			set_err("hmp_set_mapgrid(%d) has not been called for the current costmap", g);
+			return HMP_E_NOT_READY;
+		}
+	}
+	CU(cudaSetDevice(ctx->device));
+	if ((rc = resolve_wavefronts(ctx))) return rc;
+	DevParams D;
+	if ((rc = debug_params(ctx, D))) return rc;
+	const size_t n = (size_t)ctx->size_x * ctx->size_y;
+	if ((rc = ctx->d_dbg.ensure(n * 6 * sizeof(float) + n))) return rc;
+	float* d_out = (float*)ctx->d_dbg.p;
+	uint8_t* d_valid = (uint8_t*)(d_out + n * 6);
+	cudaStream_t st = ctx->stream;
+	CU(hmp_dev_launch_cost_cloud((const DevParams*)ctx->d_params.p, (int)n, (const uint8_t*)ctx->d_costmaps.p,
+	                             (const float*)ctx->d_mapgrids.p, ctx->hv_prev, d_out, d_valid, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(cloud6, d_out, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return HMP_OK;
 }

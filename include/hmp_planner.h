@@ -358,6 +358,15 @@ int hmp_get_explored_totals(HmpContext* ctx, double* totals, int32_t n);
 int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n,
                 double* costs_out, double* seeds_out, double* poses_out, int32_t* n_steps_out);
 
+/* ---- diagnostics grids ------------------------------------------------------------------------ */
+/* Replaces the per-cell loop of HumapPlannerROS::createCostGridPcl (src/humap_planner_ros.cpp:923-969) over
+ * HumapPlanner::computeCellCost (src/humap_planner.cpp:535-576): for every costmap cell c = cy * size_x + cx,
+ * cloud6[c] = {total, path, goal, layered (occ), alignment, goal_front} (scaled, FP32 like the reference's floats) and
+ * valid[c] = 1, or valid[c] = 0 where computeCellCost returns false (a MapGrid value is obstacle / unreachable, or the
+ * footprint at the cell centre with yaw 0 is in collision). Uses the costmap, MapGrids, footprint and scales currently
+ * set. The caller emits the valid cells in the reference's order (cx outer, cy inner) to build the point cloud. */
+int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid);
+
 /* ---- device-side helpers exposed for bit-exact parity tests (no reference counterpart) -------- */
 /* costmap_2d::Costmap2D::worldToMap on the device for n points; ok[i] = 0/1. */
 int hmp_debug_world_to_map(HmpContext* ctx, const double* wx, const double* wy, int32_t n,

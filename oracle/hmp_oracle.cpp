@@ -2084,6 +2084,58 @@ int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	return 0;
 }
 
+// src/humap_planner.cpp:535-576 over every cell; getFootprintCost(px, py): obstacle_separation_cost_function.cpp:134-145
+int orc_cost_cloud(const OrcPlanInput* in, float* cloud6, uint8_t* valid) {
+	const HmpCosts& C = in->params->costs;
+	Costmap cm{in->cells, in->size_x, in->size_y, in->origin_x, in->origin_y, in->resolution};
+	std::vector<double> spec(in->footprint_xy, in->footprint_xy + 2 * in->n_footprint);
+	MapGridCritic grids[HMP_NUM_MAPGRIDS];
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		grids[g].target_dist = in->target_dist[g];
+		grids[g].size_x = in->size_x;
+		grids[g].size_y = in->size_y;
+		grids[g].n_kernel_size = C.neighbour_kernel_size[g];
+		grids[g].n_cost_multiplier = C.neighbour_cost_multiplier[g];
+		grids[g].highest_valid_cost_prev = in->highest_valid_cost_prev[g];
+	}
+	for (int cy = 0; cy < in->size_y; ++cy) {
+		for (int cx = 0; cx < in->size_x; ++cx) {
+			const size_t c = (size_t)cy * in->size_x + cx;
+			float path_cost = grids[HMP_GRID_PATH].getCellCosts(cx, cy);
+			float goal_cost = grids[HMP_GRID_GOAL].getCellCosts(cx, cy);
+			double wx, wy;
+			cm.mapToWorld(cx, cy, wx, wy);
+			float occ_cost = spec.empty() ? -9.0f
+			                              : (float)obstacleFootprintCost(cm, wx, wy, 0.0, C.occdist_separation, C.occdist_separation_kernel, spec);
+			float align_cost = grids[HMP_GRID_ALIGNMENT].getCellCosts(cx, cy);
+			float goal_front_cost = grids[HMP_GRID_GOAL_FRONT].getCellCosts(cx, cy);
+			bool unreachable = false;
+			const float gv[4] = {path_cost, goal_cost, align_cost, goal_front_cost};
+			for (int k = 0; k < 4; ++k)
+				unreachable = unreachable || gv[k] == grids[k].obstacleCosts() || gv[k] == grids[k].unreachableCellCosts();
+			unreachable = unreachable || occ_cost >= 254 || occ_cost < 0;
+			valid[c] = unreachable ? 0 : 1;
+			float* o = cloud6 + c * 6;
+			if (unreachable) {
+				for (int k = 0; k < 6; ++k) o[k] = 0.0f;
+				continue;
+			}
+			path_cost *= C.scale[HMP_COST_PATH];
+			goal_cost *= C.scale[HMP_COST_GOAL];
+			occ_cost *= C.scale[HMP_COST_OBSTACLE];
+			align_cost *= C.scale[HMP_COST_ALIGNMENT];
+			goal_front_cost *= C.scale[HMP_COST_GOAL_FRONT];
+			o[0] = path_cost + goal_cost + occ_cost + align_cost + goal_front_cost;
+			o[1] = path_cost;
+			o[2] = goal_cost;
+			o[3] = occ_cost;
+			o[4] = align_cost;
+			o[5] = goal_front_cost;
+		}
+	}
+	return 0;
+}
+
 // Scores ONE externally supplied trajectory (poses [n][3], seed twist, dt = sim_time / steps) with all critics
 // in the reference order, no early exit: used to check the CUDA critics on the CUDA path's own poses.
 int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, const double seed[3], double* raw_costs,

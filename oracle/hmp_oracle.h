@@ -55,6 +55,9 @@ typedef struct OrcPlanOutput {
 int orc_plan(const OrcPlanInput* in, OrcPlanOutput* out);
 int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, const double seed[3], double* raw_costs,
                          double* total, double* hv_out);
+/* HumapPlanner::computeCellCost for every cell (src/humap_planner.cpp:535-576): cloud6[cy * size_x + cx] = {total, path,
+ * goal, layered, alignment, goal_front} floats, valid = 0 where the reference returns false */
+int orc_cost_cloud(const OrcPlanInput* in, float* cloud6, uint8_t* valid);
 int orc_num_candidates(const HmpSampling* sampling, int n_extra);
 /* velocity samples of the equisampled generator for this cycle: out[n][3] floats stored as doubles; returns n */
 int orc_equisampled_samples(const HmpParams* P, const HmpWorld* w, const HmpEquisampled* eq, double* out, int cap);

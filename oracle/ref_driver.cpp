@@ -358,6 +358,82 @@ int ref_plan(const OrcPlanInput* in, OrcPlanOutput* out) {
 	return 0;
 }
 
+// HumapPlanner::computeCellCost (reference src/humap_planner.cpp:535-576, restated here because humap_planner.cpp itself is
+// not part of this build) over the reference's own critics: humap MapGridCostFunction::getCellCosts,
+// ObstacleSeparationCostFunction::getFootprintCost(px, py). Same contract as orc_cost_cloud.
+int ref_cost_cloud(const OrcPlanInput* in, float* cloud6, uint8_t* valid) {
+	const HmpCosts& C = in->params->costs;
+	costmap_2d::Costmap2D costmap(in->cells, (unsigned)in->size_x, (unsigned)in->size_y, in->resolution, in->origin_x, in->origin_y);
+	hlp::ObstacleSeparationCostFunction obstacle_costs(&costmap);
+	base_local_planner::MapGridCostFunction path_costs(&costmap);
+	base_local_planner::MapGridCostFunction goal_costs(&costmap, 0.0, 0.0, true);
+	RefMapGridCost alignment_costs(&costmap);
+	RefMapGridCost goal_front_costs(&costmap, 0.0, 0.0, true);
+	std::vector<geometry_msgs::Point> footprint;
+	for (int i = 0; i < in->n_footprint; ++i) {
+		geometry_msgs::Point p;
+		p.x = in->footprint_xy[2 * i];
+		p.y = in->footprint_xy[2 * i + 1];
+		footprint.push_back(p);
+	}
+	obstacle_costs.setParams(in->params->limits.max_vel_trans, 0.2, 0.25, C.occdist_separation, (unsigned short)C.occdist_separation_kernel);
+	obstacle_costs.setFootprint(footprint);
+	RefMapGridCost* custom[2] = {&alignment_costs, &goal_front_costs};
+	const int slot[2] = {HMP_GRID_ALIGNMENT, HMP_GRID_GOAL_FRONT};
+	for (int k = 0; k < 2; ++k) {
+		custom[k]->setKernelSize((unsigned int)C.neighbour_kernel_size[slot[k]]);
+		custom[k]->setNeighborCellCostMultiplier(C.neighbour_cost_multiplier[slot[k]]);
+		custom[k]->seedHighestValidCost(in->highest_valid_cost_prev[slot[k]]);
+	}
+	path_costs.setScale(C.scale[HMP_COST_PATH]);
+	goal_costs.setScale(C.scale[HMP_COST_GOAL]);
+	obstacle_costs.setScale(C.scale[HMP_COST_OBSTACLE]);
+	alignment_costs.setScale(C.scale[HMP_COST_ALIGNMENT]);
+	goal_front_costs.setScale(C.scale[HMP_COST_GOAL_FRONT]);
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) g_fill_grids[g] = in->target_dist[g];
+	g_fill_next = 0;
+	base_local_planner::MapGrid::fillHook() = fillGrid;
+	path_costs.prepare();
+	goal_costs.prepare();
+	alignment_costs.prepare();
+	goal_front_costs.prepare();
+	base_local_planner::MapGrid::fillHook() = nullptr;
+	for (int cy = 0; cy < in->size_y; ++cy) {
+		for (int cx = 0; cx < in->size_x; ++cx) {
+			const size_t c = (size_t)cy * in->size_x + cx;
+			float path_cost = path_costs.getCellCosts(cx, cy);
+			float goal_cost = goal_costs.getCellCosts(cx, cy);
+			float occ_cost = obstacle_costs.getFootprintCost((unsigned)cx, (unsigned)cy);
+			float align_cost = alignment_costs.getCellCosts(cx, cy);
+			float goal_front_cost = goal_front_costs.getCellCosts(cx, cy);
+			bool cell_unreachable = path_cost == path_costs.obstacleCosts() || path_cost == path_costs.unreachableCellCosts() ||
+			                        goal_cost == goal_costs.obstacleCosts() || goal_cost == goal_costs.unreachableCellCosts() ||
+			                        occ_cost >= costmap_2d::LETHAL_OBSTACLE || occ_cost < costmap_2d::FREE_SPACE ||
+			                        align_cost == alignment_costs.obstacleCosts() || align_cost == alignment_costs.unreachableCellCosts() ||
+			                        goal_front_cost == goal_front_costs.obstacleCosts() ||
+			                        goal_front_cost == goal_front_costs.unreachableCellCosts();
+			valid[c] = cell_unreachable ? 0 : 1;
+			float* o = cloud6 + c * 6;
+			if (cell_unreachable) {
+				for (int k = 0; k < 6; ++k) o[k] = 0.0f;
+				continue;
+			}
+			path_cost *= path_costs.getScale();
+			goal_cost *= goal_costs.getScale();
+			occ_cost *= obstacle_costs.getScale();
+			align_cost *= alignment_costs.getScale();
+			goal_front_cost *= goal_front_costs.getScale();
+			o[0] = path_cost + goal_cost + occ_cost + align_cost + goal_front_cost;
+			o[1] = path_cost;
+			o[2] = goal_cost;
+			o[3] = occ_cost;
+			o[4] = align_cost;
+			o[5] = goal_front_cost;
+		}
+	}
+	return 0;
+}
+
 // fuzz::Processor::process for one tuple; out3 = (value, membership, 1 if a term fired else 0). Same contract as
 // orc_fis_process.
 void ref_fis_process(double dir_alpha, double dir_beta, double rel_loc, double dist_angle, double out3[3]) {

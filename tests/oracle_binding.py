@@ -201,6 +201,20 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     return arrs
 
 
+def cost_cloud(params: HmpParams, scene: Scene, sampling: HmpSampling, impl: str = "oracle"):
+    """HumapPlanner::computeCellCost per cell: (cloud [size_y][size_x][6] float32, valid [size_y][size_x] bool)."""
+    L = lib() if impl == "oracle" else ref_lib()
+    fn = L.orc_cost_cloud if impl == "oracle" else L.ref_cost_cloud
+    fn.argtypes = [C.POINTER(OrcPlanInput), C.c_void_p, C.c_void_p]
+    fn.restype = C.c_int
+    inp = _make_input(params, scene, sampling, None, 0, False, (0, 0))
+    n = scene.size_x * scene.size_y
+    out = np.zeros((n, 6), dtype=np.float32)
+    valid = np.zeros(n, dtype=np.uint8)
+    assert fn(C.byref(inp), _p(out), _p(valid)) == 0
+    return out.reshape(scene.size_y, scene.size_x, 6), valid.reshape(scene.size_y, scene.size_x).astype(bool)
+
+
 def plan_sampled(params, scene, sampling, indices, equisampled=None):
     """Oracle results for an explicit list of candidate indices (one orc_plan call per candidate)."""
     out = {"totals": [], "costs": [], "poses": [], "seeds": [], "n_poses": []}

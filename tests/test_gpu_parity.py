@@ -860,3 +860,23 @@ def test_equisampled_off_is_the_default_and_changes_nothing(planner):
     assert r0.n_candidates == r0.n_social == 72 and r1.n_social == 72 and r1.n_candidates > 72 and r2.n_candidates == 72
     assert np.array_equal(t0, t1[:72]) and r2.best_index == r0.best_index and r2.best_total == r0.best_total
     assert r1.n_generated >= r0.n_generated and r1.n_valid >= r0.n_valid
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" row 4: diagnostics -- the cost cloud (HumapPlanner::computeCellCost per cell) on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,seed,variant", [("cfg0", 0, "default"), ("cfg0", 1, "default"), ("cfg1", 2, "cross"),
+                                                ("cfg2", 0, "default"), ("cfg2", 3, "pentagon")])
+def test_cost_cloud_bit_exact(planner, name, seed, variant):
+    def mutate(p, sc):
+        if variant == "cross":
+            p.costs.occdist_separation_kernel = 0
+            p.costs.occdist_separation = 0.1
+        if variant == "pentagon":
+            sc.footprint = np.ascontiguousarray(_pentagon())
+    cfg, sc, params, smp = _setup(planner, name, seed, mutate=mutate)
+    g, gv = planner.cost_cloud()
+    o, ov = ob.cost_cloud(params, sc, smp)
+    assert gv.sum() > 1000 and (~gv).sum() > 1000
+    assert np.array_equal(gv, ov)
+    assert np.array_equal(g, o)      # integer-valued costs times FP64 scales rounded to float, summed in float: exact
