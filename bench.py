@@ -161,6 +161,107 @@ def _workload_name(cfg, args):
             f"FIS {'on' if args.fis else 'off'}")
 
 
+def _make_scene_job(a):
+    from humap_local_planner_b200 import scenes
+    name, seed = a
+    sc = scenes.make_scene(scenes.CONFIGS[name], seed)
+    w = sc.world
+    flat = dict(world=[w.robot_x, w.robot_y, w.robot_yaw, w.vel_x, w.vel_y, w.vel_th, w.goal_local_x, w.goal_local_y,
+                       w.goal_local_yaw, w.goal_x, w.goal_y, w.goal_yaw],
+                obstacles=bytes(memoryview(sc._obstacles))[: w.n_obstacles * 80], n_obstacles=w.n_obstacles,
+                people=bytes(memoryview(sc._people))[: w.n_people * 80], n_people=w.n_people,
+                groups=bytes(memoryview(sc._groups))[: w.n_groups * 64], n_groups=w.n_groups,
+                cells=sc.cells, grids=[g.astype(np.float32) for g in sc.grids], hv=sc.hv_prev)
+    return flat
+
+
+def run_batched(args, rank, local_rank, world, barrier):
+    """BASELINE config 4: `--scenes` independent worlds x cfg3's 4096 candidates each, scene s -> rank s mod N, one
+    hmp_plan_batch launch per rank per step, host gather of the per-scene argmins (no collective on the data path).
+    Total work is fixed, so this is STRONG scaling."""
+    import ctypes as Cc
+    import multiprocessing as mp
+    import torch
+    from humap_local_planner_b200 import Planner, scenes, capi
+    from humap_local_planner_b200.sharding import scenes_for_rank, gather_scene_results
+    cfg = scenes.CONFIGS[args.cfg]
+    S = args.scenes
+    mine = scenes_for_rank(S, rank, world)
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        flats = pool.map(_make_scene_job, [(args.cfg, s) for s in mine], chunksize=4)
+    worlds, keep = [], []
+    for f in flats:
+        w = capi.HmpWorld()
+        (w.robot_x, w.robot_y, w.robot_yaw, w.vel_x, w.vel_y, w.vel_th, w.goal_local_x, w.goal_local_y, w.goal_local_yaw,
+         w.goal_x, w.goal_y, w.goal_yaw) = f["world"]
+        ob = (capi.HmpObstacle * max(1, f["n_obstacles"])).from_buffer_copy(f["obstacles"].ljust(80 * max(1, f["n_obstacles"]), b"\0"))
+        pe = (capi.HmpPerson * max(1, f["n_people"])).from_buffer_copy(f["people"].ljust(80 * max(1, f["n_people"]), b"\0"))
+        gr = (capi.HmpGroup * max(1, f["n_groups"])).from_buffer_copy(f["groups"].ljust(64 * max(1, f["n_groups"]), b"\0"))
+        w.obstacles, w.people, w.groups = ob, pe, gr
+        w.n_obstacles, w.n_people, w.n_groups = f["n_obstacles"], f["n_people"], f["n_groups"]
+        keep.append((ob, pe, gr))
+        worlds.append(w)
+    cells = np.stack([f["cells"] for f in flats])
+    grids = [np.stack([f["grids"][g] for f in flats]).astype(np.float64) for g in range(4)]
+    hv = np.array([f["hv"] for f in flats])
+    first = scenes.make_scene(cfg, mine[0])
+    params = scenes.make_params(cfg, fis=bool(args.fis))
+    sampling = scenes.make_sampling(cfg)
+    pl = Planner(local_rank)
+    pl.set_precision(int(args.precise))
+    pl.set_params(params)
+    pl.set_scene(first)
+    n_local = len(mine)
+    res = pl.plan_batch(worlds, cells, grids, sampling, hv_prev=hv)
+    C = res[0].n_candidates
+    for _ in range(max(1, args.warmup - 1)):
+        pl.replan_resident(n_local)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pl.launch_count()
+    dev_ms = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        dev_ms.append(pl.replan_resident(n_local)[0].gpu_ms)   # per-step inputs (n_local x 680 kB) exceed the 126 MB L2
+    barrier()
+    launches = pl.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = torch.tensor([sum(dev_ms) * 1e-3], dtype=torch.float64, device="cuda")
+    e2e_t = []
+    for _ in range(min(args.steps, 3)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = pl.plan_batch(worlds, cells, grids, sampling, hv_prev=hv)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    t_e2e = torch.tensor([statistics.mean(e2e_t)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    # host gather of the per-scene argmins (16 bytes per scene)
+    gathered = gather_scene_results({s: (r.best_index, r.best_total) for s, r in zip(mine, res)}, S)
+    if rank == 0:
+        n_cells = cells[0].size
+        line = {
+            "metric": METRIC, "value": S * C * args.steps / float(t_dev.item()), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(t_dev.item()) / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": {0: "f32", 1: "f64", 2: "f32 sweep + f64 refinement of the leaders"}[int(args.precise)],
+            "data": "synthetic",
+            "config": {"workload": f"batched scenes: {S} independent worlds x {C} candidates ({_workload_name(cfg, args)})",
+                       "parallelism": f"scene s -> rank s mod {world}, one hmp_plan_batch launch per rank, host gather of argmins, no collective",
+                       "l2": f"inputs per step ({n_local} scenes x {(n_cells * 17) // 1024} kB) exceed L2", "timing": "CUDA events on the launching stream"},
+            "e2e": {"value": S * C / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(n_local * n_cells * 17),
+                    "d2h_bytes_per_step": int(n_local * Cc.sizeof(capi.HmpResult))},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "scenes_with_valid_winner": int(sum(1 for b, _ in gathered if b >= 0)),
+        }
+        print(json.dumps(line))
+    pl.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +271,9 @@ def main():
     ap.add_argument("--cfg", default="cfg2")
     ap.add_argument("--fis", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scenes", type=int, default=0,
+                    help="batched-scenes mode (BASELINE config 4, use with --cfg cfg3): this many independent worlds in total, "
+                         "sharded over the ranks, one hmp_plan_batch launch per rank per step; 0 = single-scene mode")
     ap.add_argument("--precise", type=int, default=2, help="hmp_set_precision mode: 0 FP32 object loops, 1 FP64 (exact-parity mode), 2 FP32 sweep + FP64 refinement of the leaders")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -196,6 +300,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.scenes > 0:
+        run_batched(args, rank, local_rank, world, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cfg = scenes.CONFIGS[args.cfg]
     # independent scenes are sharded over ranks (scene s -> rank s mod N), one scene per rank per step: weak scaling

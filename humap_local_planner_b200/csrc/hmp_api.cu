@@ -608,7 +608,19 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	// persistent blocks: fill the GPU once; with many scenes give each scene fewer blocks
 	long long resident = (long long)ctx->sm_count * bps;
 	long long need = ((long long)C + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK;
-	long long per_scene = std::max<long long>(1, std::min<long long>(need, (resident + pl.n_scenes - 1) / pl.n_scenes));
+	// blocks per scene: one scene fills the GPU once; with several scenes per launch pick the split p that minimises the
+	// number of block waves times the work per block, ceil(n_scenes * p / resident) / p (ties: the finer split)
+	long long per_scene = std::max<long long>(1, std::min<long long>(need, resident));
+	if (pl.n_scenes > 1) {
+		double best_t = 1e300;
+		for (long long p = 1; p <= std::min<long long>(need, 8); ++p) {
+			const double t = (double)((pl.n_scenes * p + resident - 1) / resident) / (double)p;
+			if (t <= best_t * (1.0 + 1e-12)) {
+				best_t = t;
+				per_scene = p;
+			}
+		}
+	}
 	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes\n", smem, bps, per_scene, pl.n_scenes);
 	*blocks_x_out = (int)per_scene;
 	*smem_out = smem;
