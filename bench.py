@@ -407,6 +407,15 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:   # DRAM bytes per launch of the dominant kernel from the latest committed ncu --set full capture
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+            tj = json.load(open(tf))
+            if args.cfg == "cfg2":
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except Exception:
+            pass
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_fp32 = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         line = {
@@ -424,7 +433,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32-cuda-core", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp32, "traffic": None,
+                         "frac": achieved / peak_fp32, "traffic": traffic,
                          "note": f"algorithmic flop per candidate-step W={W} (SURVEY.md 8d formula), per candidate T*W+60; dominant kernel "
                                  f"plan_kernel<false,float> avg {1e3 * sel_s:.3f} ms; peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz "
                                  "(MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is not HBM- or tensor-bound)"},
