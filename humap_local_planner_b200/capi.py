@@ -114,6 +114,22 @@ class HmpResult(C.Structure):
     ]
 
 
+class HmpShape(C.Structure):
+    """One obstacle of the costmap_converter container (teb point / circle / line / polygon)."""
+    _fields_ = [("type", _i), ("n_vertices", _i), ("first_vertex", _i), ("_pad", _i), ("x", _d), ("y", _d), ("x2", _d), ("y2", _d),
+                ("radius", _d), ("vx", _d), ("vy", _d)]
+
+
+class HmpEnvParams(C.Structure):
+    _fields_ = [("robot_model", _i), ("obstacles_closest_num", _i), ("people_closest_num", _i), ("groups_closest_num", _i),
+                ("robot_radius", _d), ("person_model_radius", _d), ("obstacle_extension_multiplier", _d),
+                ("ttc_collision_distance", _d), ("person_containment_rate", _d), ("obstacles_force_dynamic", _i),
+                ("people_force_dynamic", _i)]
+
+
+SHAPE_POINT, SHAPE_CIRCLE, SHAPE_LINE, SHAPE_POLYGON = 0, 1, 2, 3
+
+
 class HmpEquisampled(C.Structure):
     """TrajectoryGeneration's equisampled-velocity generator (humap_config.h:154-174)."""
     _fields_ = [("enabled", _i), ("vx_samples", _i), ("vy_samples", _i), ("vth_samples", _i), ("min_vel_x", _d),
@@ -126,7 +142,7 @@ ABI_SYMBOLS = (
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
-    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud",
+    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -180,6 +196,13 @@ def load_library() -> C.CDLL:
     lib.hmp_set_refinement.restype = C.c_int
     lib.hmp_set_equisampled.argtypes = [C.c_void_p, C.c_void_p]
     lib.hmp_set_equisampled.restype = C.c_int
+    lib.hmp_build_environment.argtypes = [C.c_void_p, P(HmpEnvParams), C.c_void_p, C.c_void_p, C.c_void_p, _i, C.c_void_p, _i,
+                                          C.c_void_p, _i, C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    lib.hmp_build_environment.restype = C.c_int
+    lib.hmp_compute_force_grid.argtypes = [C.c_void_p, P(HmpEnvParams), P(HmpWorld), C.c_void_p, _i, C.c_void_p, _i, C.c_void_p, _i,
+                                           C.c_void_p]
+    lib.hmp_compute_force_grid.restype = C.c_int
     lib.hmp_compute_cost_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hmp_compute_cost_cloud.restype = C.c_int
     lib.hmp_last_num_leaders.argtypes = [C.c_void_p]
@@ -219,6 +242,28 @@ class Scene:
         self.grids = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
         self.footprint = np.ascontiguousarray(footprint, dtype=np.float64)
         self.hv_prev = tuple(float(v) for v in hv_prev)
+
+
+def _build_environment(fn, ctx, check, env, robot_pose, pose_ref, shapes, vertices, people, groups):
+    """Shared marshalling of hmp_build_environment / orc_build_environment (same argument list after the context)."""
+    rp = np.ascontiguousarray(robot_pose, dtype=np.float64)
+    pr = np.ascontiguousarray(pose_ref, dtype=np.float64)
+    verts = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 2)
+    ns = len(shapes) if shapes is not None else 0
+    n_p = len(people) if people is not None else 0
+    n_g = len(groups) if groups is not None else 0
+    cap = ns + n_p
+    out = (HmpObstacle * max(1, cap))()
+    n_out = C.c_int32(cap)
+    psel = np.zeros(max(1, n_p), dtype=np.int32)
+    gsel = np.zeros(max(1, n_g), dtype=np.int32)
+    n_ps, n_gs = C.c_int32(0), C.c_int32(0)
+    args = [C.byref(env), _ptr(rp), _ptr(pr), C.cast(shapes, C.c_void_p) if ns else None, ns, _ptr(verts) if verts.size else None,
+            verts.shape[0], C.cast(people, C.c_void_p) if n_p else None, n_p, C.cast(groups, C.c_void_p) if n_g else None, n_g,
+            C.cast(out, C.c_void_p), C.byref(n_out), _ptr(psel), C.byref(n_ps), _ptr(gsel), C.byref(n_gs)]
+    rc = fn(ctx, *args) if ctx is not None else fn(*args)
+    check(rc)
+    return out, n_out.value, psel[:n_ps.value].copy(), gsel[:n_gs.value].copy()
 
 
 class Planner:
@@ -268,6 +313,23 @@ class Planner:
         valid = np.zeros(n, dtype=np.uint8)
         self._check(self._lib.hmp_compute_cost_cloud(self._ctx, _ptr(out), _ptr(valid)))
         return out.reshape(self._size_y, self._size_x, 6), valid.reshape(self._size_y, self._size_x).astype(bool)
+
+    def build_environment(self, env: HmpEnvParams, robot_pose, pose_ref, shapes, vertices: np.ndarray, people, groups):
+        """HumapPlanner::createEnvironmentModel on the device. shapes / people / groups: ctypes arrays (or None).
+        Returns (obstacles ctypes array, n_obstacles, selected people indices, selected group indices)."""
+        return _build_environment(self._lib.hmp_build_environment, self._ctx, self._check, env, robot_pose, pose_ref, shapes, vertices,
+                                  people, groups)
+
+    def force_grid(self, env: HmpEnvParams, world: HmpWorld, positions: np.ndarray, shapes, vertices: np.ndarray) -> np.ndarray:
+        """HumapPlanner::computeForceAtPosition for every position: [n][8] (internal, dynamic, static, human-action xy)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 2)
+        verts = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((pos.shape[0], 8))
+        ns = len(shapes) if shapes is not None else 0
+        self._check(self._lib.hmp_compute_force_grid(self._ctx, C.byref(env), C.byref(world), _ptr(pos), pos.shape[0],
+                                                     C.cast(shapes, C.c_void_p) if ns else None, ns,
+                                                     _ptr(verts) if verts.size else None, verts.shape[0], _ptr(out)))
+        return out
 
     def last_num_leaders(self) -> int:
         return int(self._lib.hmp_last_num_leaders(self._ctx))

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <numeric>
 #include <vector>
 
 #include "hmp_device.h"
@@ -29,6 +30,12 @@ extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_str
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_env_filter(const HmpShape* shapes, int n_shapes, const double* verts, const HmpPerson* people, int n_people,
+                                                 double person_radius, double containment_rate, double rx, double ry, int32_t* keep,
+                                                 double* metric, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_env_closest(const HmpShape* shapes, const double* verts, const HmpPerson* people, const int32_t* objects,
+                                                  int n_objects, const double* positions_xy, int n_positions, double yaw,
+                                                  const HmpEnvParams* env, HmpObstacle* out, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, uint32_t stride, float radius, uint8_t* out,
                                              int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
@@ -168,7 +175,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env;
 	HostBuf h_stage, h_out;
 	uint32_t costmap_stride = 0;
 
@@ -693,7 +700,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	ctx->h_out.release();
@@ -1513,6 +1520,255 @@ int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid) {
 	CU(cudaMemcpyAsync(cloud6, d_out, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	return HMP_OK;
+}
+
+// ---- environment model ---------------------------------------------------------------------------------------------
+namespace {
+
+// HumapPlanner::selectRelevant (humap_planner.h:387-427): everything in input order when N is negative ((size_t)-1) or not
+// smaller than the count, else the N smallest metrics (ties by input order)
+std::vector<int> select_relevant(const std::vector<double>& metric, int max_num) {
+	std::vector<int> idx(metric.size());
+	std::iota(idx.begin(), idx.end(), 0);
+	if (max_num < 0 || metric.size() <= (size_t)max_num) return idx;
+	if (max_num == 0) return {};
+	std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return metric[a] < metric[b]; });
+	idx.resize((size_t)max_num);
+	return idx;
+}
+
+struct EnvSelection {
+	std::vector<int32_t> objects;          // >= 0 shape index, < 0 person -(index + 1); World::addObstacle order
+	std::vector<int32_t> people, groups;   // people_env_model_, groups_env_model_
+	// device pointers into ctx->d_env (valid until the next call)
+	const HmpShape* d_shapes = nullptr;
+	const double* d_verts = nullptr;
+	const HmpPerson* d_people = nullptr;
+	int32_t* d_objects = nullptr;
+	double* d_positions = nullptr;
+	HmpObstacle* d_out = nullptr;
+};
+
+size_t align16(size_t v) { return (v + 15) / 16 * 16; }
+
+// uploads the inputs, filters + ranks the shapes on the device, selects on the host, uploads the object list and reserves
+// room for n_positions x objects closest-point records
+int env_select(HmpContext* ctx, const HmpEnvParams& env, const double robot_pose[3], const HmpShape* shapes, int n_shapes,
+               const double* verts, int n_verts, const HmpPerson* people, int n_people, const HmpGroup* groups, int n_groups,
+               int n_positions, EnvSelection& sel) {
+	if (env.robot_model != 0 && env.robot_model != 1) {
+		set_err("robot_model %d: only the point (0) and circular (1) footprint models are built", env.robot_model);
+		return HMP_E_INVALID;
+	}
+	for (int i = 0; i < n_shapes; ++i) {
+		const HmpShape& s = shapes[i];
+		if (s.type < HMP_SHAPE_POINT || s.type > HMP_SHAPE_POLYGON ||
+		    (s.type == HMP_SHAPE_POLYGON && (s.n_vertices < 1 || s.first_vertex < 0 || s.first_vertex + s.n_vertices > n_verts))) {
+			set_err("shape %d is malformed", i);
+			return HMP_E_INVALID;
+		}
+	}
+	const size_t b_shapes = align16(std::max(1, n_shapes) * sizeof(HmpShape));
+	const size_t b_verts = align16(std::max(1, n_verts) * 2 * sizeof(double));
+	const size_t b_people = align16(std::max(1, n_people) * sizeof(HmpPerson));
+	const size_t b_keep = align16(std::max(1, n_shapes) * sizeof(int32_t));
+	const size_t b_metric = align16(std::max(1, n_shapes) * sizeof(double));
+	const size_t n_obj_max = (size_t)n_shapes + n_people;
+	const size_t b_objects = align16(std::max<size_t>(1, n_obj_max) * sizeof(int32_t));
+	const size_t b_pos = align16(std::max(1, n_positions) * 2 * sizeof(double));
+	const size_t b_out = align16(std::max<size_t>(1, n_obj_max * n_positions) * sizeof(HmpObstacle));
+	int rc;
+	if ((rc = ctx->d_env.ensure(b_shapes + b_verts + b_people + b_keep + b_metric + b_objects + b_pos + b_out))) return rc;
+	unsigned char* base = (unsigned char*)ctx->d_env.p;
+	HmpShape* d_shapes = (HmpShape*)base;
+	double* d_verts = (double*)(base + b_shapes);
+	HmpPerson* d_people = (HmpPerson*)(base + b_shapes + b_verts);
+	int32_t* d_keep = (int32_t*)(base + b_shapes + b_verts + b_people);
+	double* d_metric = (double*)((unsigned char*)d_keep + b_keep);
+	sel.d_objects = (int32_t*)((unsigned char*)d_metric + b_metric);
+	sel.d_positions = (double*)((unsigned char*)sel.d_objects + b_objects);
+	sel.d_out = (HmpObstacle*)((unsigned char*)sel.d_positions + b_pos);
+	sel.d_shapes = d_shapes;
+	sel.d_verts = d_verts;
+	sel.d_people = d_people;
+	cudaStream_t st = ctx->stream;
+	if (n_shapes > 0) CU(cudaMemcpyAsync(d_shapes, shapes, (size_t)n_shapes * sizeof(HmpShape), cudaMemcpyHostToDevice, st));
+	if (n_verts > 0) CU(cudaMemcpyAsync(d_verts, verts, (size_t)n_verts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+	if (n_people > 0) CU(cudaMemcpyAsync(d_people, people, (size_t)n_people * sizeof(HmpPerson), cudaMemcpyHostToDevice, st));
+	std::vector<int32_t> keep((size_t)n_shapes);
+	std::vector<double> metric((size_t)n_shapes);
+	if (n_shapes > 0) {
+		CU(hmp_dev_launch_env_filter(d_shapes, n_shapes, d_verts, d_people, n_people, env.person_model_radius, env.person_containment_rate,
+		                             robot_pose[0], robot_pose[1], d_keep, d_metric, st));
+		ctx->launches++;
+		CU(cudaMemcpyAsync(keep.data(), d_keep, (size_t)n_shapes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(metric.data(), d_metric, (size_t)n_shapes * sizeof(double), cudaMemcpyDeviceToHost, st));
+	}
+	CU(cudaStreamSynchronize(st));
+	std::vector<int> kept;
+	std::vector<double> kept_metric;
+	for (int i = 0; i < n_shapes; ++i) {
+		if (keep[i]) {
+			kept.push_back(i);
+			kept_metric.push_back(metric[i]);
+		}
+	}
+	sel.objects.clear();
+	for (int k : select_relevant(kept_metric, env.obstacles_closest_num)) sel.objects.push_back(kept[k]);
+	std::vector<double> m;
+	for (int p = 0; p < n_people; ++p) m.push_back(std::hypot(people[p].x - robot_pose[0], people[p].y - robot_pose[1]));
+	sel.people.clear();
+	for (int p : select_relevant(m, env.people_closest_num)) sel.people.push_back(p);
+	m.clear();
+	for (int g = 0; g < n_groups; ++g) m.push_back(std::hypot(groups[g].x - robot_pose[0], groups[g].y - robot_pose[1]));
+	sel.groups.clear();
+	for (int g : select_relevant(m, env.groups_closest_num)) sel.groups.push_back(g);
+	for (int32_t p : sel.people) sel.objects.push_back(-(p + 1));
+	if (!sel.objects.empty())
+		CU(cudaMemcpyAsync(sel.d_objects, sel.objects.data(), sel.objects.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	return HMP_OK;
+}
+
+}  // namespace
+
+int hmp_build_environment(HmpContext* ctx, const HmpEnvParams* env, const double robot_pose[3], const double pose_ref[3],
+                          const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy, int32_t n_vertices,
+                          const HmpPerson* people, int32_t n_people, const HmpGroup* groups, int32_t n_groups,
+                          HmpObstacle* obstacles_out, int32_t* n_obstacles_out, int32_t* people_selected,
+                          int32_t* n_people_selected, int32_t* groups_selected, int32_t* n_groups_selected) {
+	if (!ctx || !env || !robot_pose || !pose_ref || n_shapes < 0 || n_vertices < 0 || n_people < 0 || n_groups < 0 ||
+	    (n_shapes > 0 && !shapes) || (n_vertices > 0 && !vertices_xy) || (n_people > 0 && !people) || (n_groups > 0 && !groups) ||
+	    !obstacles_out || !n_obstacles_out || !people_selected || !n_people_selected || !groups_selected || !n_groups_selected) {
+		set_err("bad environment arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	EnvSelection sel;
+	int rc = env_select(ctx, *env, robot_pose, shapes, n_shapes, vertices_xy, n_vertices, people, n_people, groups, n_groups, 1, sel);
+	if (rc) return rc;
+	const int n_obj = (int)sel.objects.size();
+	if (n_obj > *n_obstacles_out) {
+		set_err("environment model has %d objects, capacity %d", n_obj, *n_obstacles_out);
+		return HMP_E_CAPACITY;
+	}
+	cudaStream_t st = ctx->stream;
+	if (n_obj > 0) {
+		CU(cudaMemcpyAsync(sel.d_positions, pose_ref, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, n_obj, sel.d_positions, 1, pose_ref[2], env,
+		                              sel.d_out, st));
+		ctx->launches++;
+		CU(cudaMemcpyAsync(obstacles_out, sel.d_out, (size_t)n_obj * sizeof(HmpObstacle), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	}
+	*n_obstacles_out = n_obj;
+	std::copy(sel.people.begin(), sel.people.end(), people_selected);
+	*n_people_selected = (int)sel.people.size();
+	std::copy(sel.groups.begin(), sel.groups.end(), groups_selected);
+	*n_groups_selected = (int)sel.groups.size();
+	return HMP_OK;
+}
+
+int hmp_compute_force_grid(HmpContext* ctx, const HmpEnvParams* env, const HmpWorld* world, const double* positions_xy,
+                           int32_t n_positions, const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy,
+                           int32_t n_vertices, double* forces_out) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (!env || !world || !positions_xy || n_positions <= 0 || n_shapes < 0 || n_vertices < 0 || (n_shapes > 0 && !shapes) ||
+	    (n_vertices > 0 && !vertices_xy) || !forces_out || world->n_people < 0 || world->n_groups < 0 ||
+	    (world->n_people > 0 && !world->people) || (world->n_groups > 0 && !world->groups)) {
+		set_err("bad force-grid arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	const double robot_pose[3] = {world->robot_x, world->robot_y, world->robot_yaw};
+	EnvSelection sel;
+	if ((rc = env_select(ctx, *env, robot_pose, shapes, n_shapes, vertices_xy, n_vertices, world->people, world->n_people, world->groups,
+	                     world->n_groups, n_positions, sel)))
+		return rc;
+	const int n_obj = (int)sel.objects.size();
+	cudaStream_t st = ctx->stream;
+	std::vector<HmpObstacle> records((size_t)n_obj * n_positions);
+	if (n_obj > 0) {
+		CU(cudaMemcpyAsync(sel.d_positions, positions_xy, (size_t)n_positions * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, n_obj, sel.d_positions, n_positions,
+		                              world->robot_yaw, env, sel.d_out, st));
+		ctx->launches++;
+		CU(cudaMemcpyAsync(records.data(), sel.d_out, records.size() * sizeof(HmpObstacle), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	}
+	// one world per position: the robot there with the yaw of pose_, velocity vel_ rotated by pose_ (computeVelocityGlobal(vel_,
+	// pose_), humap_planner.cpp:654-656 -- the yaw is the same), goals unchanged; the motion model runs once with
+	// SampleAmplifierSet() and dt = sim_period (social_trajectory_generator.cpp:504-527)
+	HmpSampling unit;
+	for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) {
+		unit.amp_min[a] = unit.amp_max[a] = 1.0;
+		unit.amp_granularity[a] = 1.0;
+	}
+	DevParams D;
+	std::vector<double> amp_table;
+	if ((rc = build_dev_params(ctx, &unit, 0, 1, D, amp_table))) return rc;
+	D.dt_d = ctx->params.general.sim_period;
+	D.dt = (float)D.dt_d;
+	std::vector<HmpWorld> worlds((size_t)n_positions, *world);
+	size_t stride = 0;
+	for (int i = 0; i < n_positions; ++i) {
+		HmpWorld& w = worlds[i];
+		w.robot_x = positions_xy[2 * i];
+		w.robot_y = positions_xy[2 * i + 1];
+		w.obstacles = n_obj > 0 ? records.data() + (size_t)i * n_obj : nullptr;
+		w.n_obstacles = n_obj;
+		w.people = nullptr;
+		w.n_people = 0;
+		w.groups = nullptr;
+		w.n_groups = 0;
+		stride = std::max(stride, scene_blob_bytes(w));
+	}
+	if ((rc = ctx->d_scenes.ensure(stride * n_positions))) return rc;
+	if ((rc = ctx->h_stage.ensure(stride * n_positions))) return rc;
+	unsigned char* hs = (unsigned char*)ctx->h_stage.p;
+	std::memset(hs, 0, stride * n_positions);
+	for (int i = 0; i < n_positions; ++i) pack_scene(ctx, worlds[i], nullptr, D.dt_d, hs + stride * i);
+	CU(cudaMemcpyAsync(ctx->d_scenes.p, hs, stride * n_positions, cudaMemcpyHostToDevice, st));
+	if ((rc = ctx->d_params.ensure(sizeof(DevParams)))) return rc;
+	if ((rc = ctx->d_amp.ensure(amp_table.size() * sizeof(double)))) return rc;
+	const CtrlLayout cl = ctrl_layout(n_positions);
+	if ((rc = ctx->d_ctrl.ensure(cl.total))) return rc;
+	const size_t f_bytes = (size_t)n_positions * 8 * sizeof(double);
+	if ((rc = ctx->d_dbg.ensure(f_bytes))) return rc;
+	CU(cudaMemcpyAsync(ctx->d_params.p, &D, sizeof(DevParams), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ctx->d_amp.p, amp_table.data(), amp_table.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, cl.total, st));
+	CU(cudaMemsetAsync(ctx->d_dbg.p, 0, f_bytes, st));
+	const size_t smem = hmp_dev_smem_bytes((uint32_t)stride, 0, 0);
+	if (smem > ctx->max_smem_optin) {
+		set_err("scene does not fit shared memory");
+		return HMP_E_CAPACITY;
+	}
+	unsigned char* ctrl = (unsigned char*)ctx->d_ctrl.p;
+	KernelArgs A;
+	std::memset(&A, 0, sizeof(A));
+	A.params = (const DevParams*)ctx->d_params.p;
+	A.amp_values = (const double*)ctx->d_amp.p;
+	A.scenes = (const uint8_t*)ctx->d_scenes.p;
+	A.scene_stride = (uint32_t)stride;
+	A.n_scenes = n_positions;
+	A.costmaps = (const uint8_t*)ctx->d_costmaps.p;   // untouched: forces_only
+	A.costmap_stride = 0;
+	A.costmap_in_smem = 0;
+	A.precise = 1;                                    // diagnostics: FP64 object loops
+	A.mapgrids = (const float*)ctx->d_mapgrids.p;
+	A.n_work = 1;
+	A.forces_only = 1;
+	A.counters = (unsigned int*)(ctrl + cl.off_counters);
+	A.hv_out = (unsigned int*)(ctrl + cl.off_hv);
+	A.best_out = (double*)(ctrl + cl.off_best);
+	A.d_forces = (double*)ctx->d_dbg.p;
+	CU(hmp_dev_launch_plan(&A, 1, 1, smem, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(forces_out, ctx->d_dbg.p, f_bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	ctx->last_valid = false;
 	return HMP_OK;
 }
 

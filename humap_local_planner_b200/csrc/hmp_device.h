@@ -188,6 +188,8 @@ struct KernelArgs {
 	int32_t _pado;
 	const double* best_init;         /* [n_scenes][2] (total, index) of an earlier sweep over other candidates of the same pool, merged
 	                                    into best_out by the last block (ties: lower index wins), or null                */
+	int32_t forces_only;             /* detail launches of the force-field grid: rollout arithmetic only, no critic touches the costmap / MapGrids */
+	int32_t _padf2;
 	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
 	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
 	int32_t _padt;

@@ -281,3 +281,62 @@ def make_params(cfg: CycleConfig, fis: bool = True):
 
 def make_sampling(cfg: CycleConfig):
     return config.make_sampling(cfg.sampling)
+
+
+def make_shapes(seed: int, n: int = 40, people=None, robot_xy=(0.0, 0.0)):
+    """Synthetic costmap_converter output: a mix of point, circle, line and polygon obstacles around the robot, a few of
+    them sitting on people (legs seen by the laser) so that extractNonPeopleObstacles has something to remove.
+    Returns (ctypes array of HmpShape, vertex pool [m][2])."""
+    from .capi import HmpShape, SHAPE_POINT, SHAPE_CIRCLE, SHAPE_LINE, SHAPE_POLYGON
+    rng = np.random.default_rng(1000 + seed)
+    shapes, verts = [], []
+    rx, ry = robot_xy
+    for i in range(n):
+        s = HmpShape()
+        a, r = rng.uniform(-math.pi, math.pi), rng.uniform(0.7, 4.5)
+        cx, cy = rx + r * math.cos(a), ry + r * math.sin(a)
+        kind = i % 4
+        s.vx, s.vy = (rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3)) if i % 7 == 0 else (0.0, 0.0)
+        if kind == 0:
+            s.type, s.x, s.y = SHAPE_POINT, cx, cy
+        elif kind == 1:
+            s.type, s.x, s.y, s.radius = SHAPE_CIRCLE, cx, cy, rng.uniform(0.05, 0.3)
+        elif kind == 2:
+            th, ln = rng.uniform(-math.pi, math.pi), rng.uniform(0.2, 1.5)
+            s.type, s.x, s.y = SHAPE_LINE, cx, cy
+            s.x2, s.y2 = cx + ln * math.cos(th), cy + ln * math.sin(th)
+        else:
+            k = int(rng.integers(3, 7))
+            ang = np.sort(rng.uniform(-math.pi, math.pi, k))
+            rad = rng.uniform(0.1, 0.5, k)
+            s.type, s.first_vertex, s.n_vertices = SHAPE_POLYGON, len(verts), k
+            for t, q in zip(ang, rad):
+                verts.append((cx + q * math.cos(t), cy + q * math.sin(t)))
+        shapes.append(s)
+    if people is not None:
+        for p in list(people)[:3]:   # leg-like obstacles inside the person model radius
+            s = HmpShape()
+            s.type, s.first_vertex, s.n_vertices = SHAPE_POLYGON, len(verts), 3
+            for t in (0.0, 2.1, 4.2):
+                verts.append((p.x + 0.1 * math.cos(t), p.y + 0.1 * math.sin(t)))
+            shapes.append(s)
+            s2 = HmpShape()
+            s2.type, s2.x, s2.y = SHAPE_POINT, p.x + 0.05, p.y - 0.05
+            shapes.append(s2)
+    arr = (HmpShape * len(shapes))(*shapes)
+    return arr, np.array(verts, dtype=np.float64).reshape(-1, 2)
+
+
+def make_env_params(closest=(-1, -1, -1), robot_model: int = 1):
+    from .capi import HmpEnvParams
+    e = HmpEnvParams()
+    e.robot_model = robot_model
+    e.obstacles_closest_num, e.people_closest_num, e.groups_closest_num = closest
+    e.robot_radius = config.ROBOT_INSCRIBED_RADIUS
+    e.person_model_radius = config.PERSON_MODEL_RADIUS
+    e.obstacle_extension_multiplier = 1.0
+    e.ttc_collision_distance = 0.05
+    e.person_containment_rate = 0.667
+    e.obstacles_force_dynamic = 0
+    e.people_force_dynamic = 1
+    return e

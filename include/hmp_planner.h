@@ -249,6 +249,32 @@ typedef struct HmpEquisampled {
 	int32_t _pad;
 } HmpEquisampled;
 
+/* ---- environment model: inputs of HumapPlanner::createEnvironmentModel ------------------------- */
+/* One obstacle of the ObstContainer the planner receives from costmap_converter (teb_local_planner obstacle types
+ * wrapped by include/humap_local_planner/obstacles.h). Polygon vertices live in a shared pool (xy interleaved). */
+enum HmpShapeType { HMP_SHAPE_POINT = 0, HMP_SHAPE_CIRCLE = 1, HMP_SHAPE_LINE = 2, HMP_SHAPE_POLYGON = 3 };
+typedef struct HmpShape {
+	int32_t type;                 /* HmpShapeType                                                     */
+	int32_t n_vertices;           /* polygon: vertices in the pool; others: ignored                   */
+	int32_t first_vertex;         /* polygon: index of its first vertex in the pool                   */
+	int32_t _pad;
+	double x, y;                  /* point / circle centre / line start                               */
+	double x2, y2;                /* line end                                                         */
+	double radius;                /* circle                                                           */
+	double vx, vy;                /* getCentroidVelocity()                                            */
+} HmpShape;
+typedef struct HmpEnvParams {
+	int32_t robot_model;          /* 0 PointRobotFootprint, 1 CircularRobotFootprint (robot_footprint_model.h:55-140) */
+	int32_t obstacles_closest_num, people_closest_num, groups_closest_num;   /* GeneralParams, -1 = all   */
+	double robot_radius;          /* getInscribedRadius()                                             */
+	double person_model_radius;   /* GeneralParams::person_model_radius                               */
+	double obstacle_extension_multiplier;   /* GeneralParams                                          */
+	double ttc_collision_distance;           /* CostParams (enlargeObstacle threshold = 1.05 x this)   */
+	double person_containment_rate;          /* HumapPlanner::PERSON_POLYGON_CONTAINMENT_RATE = 0.667  */
+	int32_t obstacles_force_dynamic;         /* static_obj_interaction == INTERACTION_REPULSIVE_EVASIVE */
+	int32_t people_force_dynamic;            /* SfmParams::human_force_formulation_dynamic              */
+} HmpEnvParams;
+
 /* ---- result ------------------------------------------------------------------------------- */
 typedef struct HmpResult {
 	int32_t status;                /* 0: a valid trajectory was found; 1: none valid (cost < 0)   */
@@ -366,6 +392,29 @@ int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n,
  * footprint at the cell centre with yaw 0 is in collision). Uses the costmap, MapGrids, footprint and scales currently
  * set. The caller emits the valid cells in the reference's order (cx outer, cy inner) to build the point cloud. */
 int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid);
+
+/* Replaces HumapPlanner::createEnvironmentModel (src/humap_planner.cpp:930-1052 with extractNonPeopleObstacles :760-801,
+ * selectRelevant humap_planner.h:387-427, calculateClosestPoints robot_footprint_model.h:89-140, enlargeObstacle
+ * :681-758): filters obstacles that are really people, keeps the N closest obstacles / people / groups (metric relative to
+ * robot_pose = pose_), and computes on the device, for the robot placed at pose_ref, the closest-point pair of every kept
+ * obstacle (enlarged) and of every kept person (a circle of person_model_radius). Output = the World::addObstacle call
+ * sequence (obstacles first, then people) ready for HmpWorld.obstacles, plus the indices of the kept people / groups
+ * (people_env_model_, groups_env_model_). *n_obstacles_out holds the capacity on entry. Ties of the N-closest metric are
+ * resolved by input order (the reference's std::sort leaves them unspecified). Point and circular robot models only. */
+int hmp_build_environment(HmpContext* ctx, const HmpEnvParams* env, const double robot_pose[3], const double pose_ref[3],
+                          const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy, int32_t n_vertices,
+                          const HmpPerson* people, int32_t n_people, const HmpGroup* groups, int32_t n_groups,
+                          HmpObstacle* obstacles_out, int32_t* n_obstacles_out, int32_t* people_selected,
+                          int32_t* n_people_selected, int32_t* groups_selected, int32_t* n_groups_selected);
+/* Replaces the loop of Visualization::publishGrid (src/visualization.cpp:246-286) over
+ * HumapPlanner::computeForceAtPosition (src/humap_planner.cpp:652-678): for each of the n positions the robot is placed
+ * there with the yaw of robot_pose, the environment model is rebuilt (as above; the N-closest selection stays relative to
+ * robot_pose), and the social force model + fuzzy conductor are evaluated once with unit amplifiers and dt = sim_period
+ * (generateTrajectoryWithoutPlanning, social_trajectory_generator.cpp:504-527). forces_out[i] = {internal.xy, dynamic.xy,
+ * static.xy, human-action.xy}; the reference's force_total is their sum. world carries vel_, goal_local_, goal_. */
+int hmp_compute_force_grid(HmpContext* ctx, const HmpEnvParams* env, const HmpWorld* world, const double* positions_xy,
+                           int32_t n_positions, const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy,
+                           int32_t n_vertices, double* forces_out);
 
 /* ---- device-side helpers exposed for bit-exact parity tests (no reference counterpart) -------- */
 /* costmap_2d::Costmap2D::worldToMap on the device for n points; ok[i] = 0/1. */

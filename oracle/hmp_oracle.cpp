@@ -1673,6 +1673,197 @@ bool areVelocityLimitsFulfilled(const HmpLimits& l, double speed_linear, double 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Environment model: HumapPlanner::createEnvironmentModel (src/humap_planner.cpp:930-1052, first-party) over the
+// teb_local_planner obstacle classes [RECALLED: getClosestPoint / getMinimumDistance / toPolygonMsg of Point, Circular,
+// Line and Polygon obstacles and closest_point_on_line_segment_2d; parity unpinned] and the first-party footprint models
+// (include/humap_local_planner/robot_footprint_model.h:55-140).
+// ------------------------------------------------------------------------------------------------
+struct P2 {
+	double x, y;
+};
+inline P2 closestPointOnSegment(P2 p, P2 s, P2 e) {
+	double dx = e.x - s.x, dy = e.y - s.y;
+	double sq = dx * dx + dy * dy;
+	if (sq == 0) return s;
+	double u = ((p.x - s.x) * dx + (p.y - s.y) * dy) / sq;
+	if (u <= 0) return s;
+	if (u >= 1) return e;
+	return {s.x + u * dx, s.y + u * dy};
+}
+inline double dist2d(P2 a, P2 b) { return std::hypot(a.x - b.x, a.y - b.y); }
+
+struct ShapeView {
+	const HmpShape* s;
+	const double* verts;
+	P2 vertex(int i) const { return {verts[2 * (s->first_vertex + i)], verts[2 * (s->first_vertex + i) + 1]}; }
+	// Obstacle::getClosestPoint(position)
+	P2 closestPoint(P2 p) const {
+		switch (s->type) {
+			case HMP_SHAPE_POINT: return {s->x, s->y};
+			case HMP_SHAPE_CIRCLE: {
+				double dx = p.x - s->x, dy = p.y - s->y;
+				double n = std::sqrt(dx * dx + dy * dy);
+				return {s->x + s->radius * (dx / n), s->y + s->radius * (dy / n)};   // Eigen normalized(): 0/0 for a centre hit
+			}
+			case HMP_SHAPE_LINE: return closestPointOnSegment(p, {s->x, s->y}, {s->x2, s->y2});
+			default: {
+				const int n = s->n_vertices;
+				if (n == 1) return vertex(0);
+				P2 best = vertex(0);
+				double dmin = HUGE_VAL;
+				for (int i = 0; i < n - 1; ++i) {
+					P2 q = closestPointOnSegment(p, vertex(i), vertex(i + 1));
+					double d = dist2d(q, p);
+					if (d < dmin) { dmin = d; best = q; }
+				}
+				if (n > 2) {
+					P2 q = closestPointOnSegment(p, vertex(n - 1), vertex(0));
+					double d = dist2d(q, p);
+					if (d < dmin) { dmin = d; best = q; }
+				}
+				return best;
+			}
+		}
+	}
+	// Obstacle::getMinimumDistance(position)
+	double minimumDistance(P2 p) const {
+		switch (s->type) {
+			case HMP_SHAPE_POINT: return dist2d(p, {s->x, s->y});
+			case HMP_SHAPE_CIRCLE: return dist2d(p, {s->x, s->y}) - s->radius;
+			case HMP_SHAPE_LINE: return dist2d(p, closestPointOnSegment(p, {s->x, s->y}, {s->x2, s->y2}));
+			default: return dist2d(p, closestPoint(p));
+		}
+	}
+	// points of Obstacle::toPolygonMsg
+	int numPolygonPoints() const { return s->type == HMP_SHAPE_POLYGON ? s->n_vertices : (s->type == HMP_SHAPE_LINE ? 2 : 1); }
+	P2 polygonPoint(int i) const {
+		if (s->type == HMP_SHAPE_POLYGON) return vertex(i);
+		if (s->type == HMP_SHAPE_LINE && i == 1) return {s->x2, s->y2};
+		return {s->x, s->y};
+	}
+};
+
+// BaseRobotFootprintModel::calculateClosestPoints for the point and the circular model (robot_footprint_model.h:89-140)
+inline void calculateClosestPoints(const HmpEnvParams& env, const double pose[3], P2 obstacle_pt, Pose& robot_out, Pose& obstacle_out) {
+	obstacle_out = Pose(obstacle_pt.x, obstacle_pt.y, 0.0);
+	if (env.robot_model == 0) {
+		robot_out = Pose(pose[0], pose[1], pose[2]);
+		return;
+	}
+	double vx = obstacle_pt.x - pose[0], vy = obstacle_pt.y - pose[1];
+	double n = std::sqrt(vx * vx + vy * vy);
+	robot_out = Pose(pose[0] + (vx / n) * env.robot_radius, pose[1] + (vy / n) * env.robot_radius, pose[2]);
+}
+
+// HumapPlanner::enlargeObstacle, src/humap_planner.cpp:681-758
+bool enlargeObstacle(const Pose& robot_pt, Pose& obstacle_pt, double extension_distance, double distance_collision_imminent) {
+	if (extension_distance <= 0.0) return false;
+	V3 dist_init{obstacle_pt.x - robot_pt.x, obstacle_pt.y - robot_pt.y, 0.0};
+	if (len3(dist_init) <= distance_collision_imminent) return false;
+	double dist_init_dir = std::atan2(dist_init.y, dist_init.x);   // Angle(Vector): not normalised further
+	V3 ext{std::cos(dist_init_dir) * extension_distance, std::sin(dist_init_dir) * extension_distance, 0.0};
+	Pose hypothesis(obstacle_pt.x - ext.x, obstacle_pt.y - ext.y, obstacle_pt.yaw);
+	V3 dist_modded{hypothesis.x - robot_pt.x, hypothesis.y - robot_pt.y, 0.0};
+	double dist_angle_diff = std::abs(std::atan2(dist_modded.y, dist_modded.x) - dist_init_dir);
+	if (dist_angle_diff <= dtor(1.0)) {
+		obstacle_pt = hypothesis;
+		return true;
+	}
+	// fallback stage: the reference re-measures the ORIGINAL closest-point vector here (:744-748), so the test always
+	// passes and the obstacle point is placed at the collision distance from the robot point
+	hypothesis = Pose(robot_pt.x + distance_collision_imminent * std::cos(dist_init_dir),
+	                  robot_pt.y + distance_collision_imminent * std::sin(dist_init_dir), obstacle_pt.yaw);
+	dist_modded = {obstacle_pt.x - robot_pt.x, obstacle_pt.y - robot_pt.y, 0.0};
+	dist_angle_diff = std::abs(std::atan2(dist_modded.y, dist_modded.x) - dist_init_dir);
+	if (dist_angle_diff <= dtor(1.0)) {
+		obstacle_pt = hypothesis;
+		return true;
+	}
+	return false;
+}
+
+// HumapPlanner::selectRelevant (humap_planner.h:387-427); ties keep the input order (std::sort leaves them unspecified)
+std::vector<int> selectRelevant(const std::vector<double>& metric, int max_object_num) {
+	std::vector<int> idx(metric.size());
+	for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+	if (max_object_num < 0 || metric.size() <= (size_t)max_object_num) return idx;   // (size_t)-1: everything, input order
+	if (max_object_num == 0) return {};
+	std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return metric[a] < metric[b]; });
+	idx.resize((size_t)max_object_num);
+	return idx;
+}
+
+struct EnvModel {
+	std::vector<HmpObstacle> obstacles;   // World::addObstacle call order
+	std::vector<int> people, groups;      // people_env_model_, groups_env_model_
+};
+
+EnvModel createEnvironmentModel(const HmpEnvParams& env, const double robot_pose[3], const double pose_ref[3], const HmpShape* shapes,
+                                int n_shapes, const double* verts, const HmpPerson* people, int n_people, const HmpGroup* groups,
+                                int n_groups) {
+	EnvModel m;
+	// extractNonPeopleObstacles (:760-801)
+	std::vector<int> kept;
+	for (int i = 0; i < n_shapes; ++i) {
+		ShapeView sv{&shapes[i], verts};
+		double max_rate = -1.0;
+		for (int p = 0; p < n_people; ++p) {
+			int within = 0;
+			const int np = sv.numPolygonPoints();
+			for (int k = 0; k < np; ++k) {
+				P2 pt = sv.polygonPoint(k);
+				if (std::hypot(pt.x - people[p].x, pt.y - people[p].y) <= env.person_model_radius) within++;
+			}
+			max_rate = std::max(max_rate, (double)within / np);
+		}
+		if (n_people > 0 && max_rate >= env.person_containment_rate) continue;
+		kept.push_back(i);
+	}
+	// N closest obstacles / people / groups relative to pose_ (:940-980)
+	std::vector<double> metric;
+	for (int i : kept) metric.push_back(ShapeView{&shapes[i], verts}.minimumDistance({robot_pose[0], robot_pose[1]}));
+	std::vector<int> obs_sel = selectRelevant(metric, env.obstacles_closest_num);
+	metric.clear();
+	for (int p = 0; p < n_people; ++p) metric.push_back(len3({people[p].x - robot_pose[0], people[p].y - robot_pose[1], 0.0}));
+	m.people = selectRelevant(metric, env.people_closest_num);
+	metric.clear();
+	for (int g = 0; g < n_groups; ++g) metric.push_back(len3({groups[g].x - robot_pose[0], groups[g].y - robot_pose[1], 0.0}));
+	m.groups = selectRelevant(metric, env.groups_closest_num);
+	auto emit = [&](const Pose& r, const Pose& o, double vx, double vy, double vth, bool force_dynamic) {
+		HmpObstacle ob;
+		std::memset(&ob, 0, sizeof(ob));
+		ob.robot_x = r.x; ob.robot_y = r.y; ob.robot_yaw = r.yaw;
+		ob.obj_x = o.x; ob.obj_y = o.y; ob.obj_yaw = o.yaw;
+		ob.vx = vx; ob.vy = vy; ob.vth = vth;
+		ob.force_dynamic = force_dynamic ? 1 : 0;
+		m.obstacles.push_back(ob);
+	};
+	// :983-1025
+	for (int k : obs_sel) {
+		const HmpShape& sh = shapes[kept[k]];
+		ShapeView sv{&sh, verts};
+		Pose r, o;
+		calculateClosestPoints(env, pose_ref, sv.closestPoint({pose_ref[0], pose_ref[1]}), r, o);
+		enlargeObstacle(r, o, env.obstacle_extension_multiplier * env.robot_radius, 1.05 * env.ttc_collision_distance);
+		emit(r, o, sh.vx, sh.vy, 0.0, env.obstacles_force_dynamic != 0);
+	}
+	// :1027-1049: a person is a CircularObstacle of person_model_radius
+	for (int p : m.people) {
+		HmpShape circle;
+		std::memset(&circle, 0, sizeof(circle));
+		circle.type = HMP_SHAPE_CIRCLE;
+		circle.x = people[p].x;
+		circle.y = people[p].y;
+		circle.radius = env.person_model_radius;
+		ShapeView sv{&circle, nullptr};
+		Pose r, o;
+		calculateClosestPoints(env, pose_ref, sv.closestPoint({pose_ref[0], pose_ref[1]}), r, o);
+		emit(r, o, people[p].vx, people[p].vy, people[p].vth, env.people_force_dynamic != 0);
+	}
+	return m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Equisampled velocities: base_local_planner::SimpleTrajectoryGenerator + VelocityIterator [RECALLED from upstream
 // ros-planning/navigation, parity unpinned] as wired by src/humap_planner.cpp:196-203 and :1317-1361 (first-party).
 // The upstream generator works on Eigen::Vector3f: positions, velocities and acceleration limits are FP32 values,
@@ -1949,6 +2140,50 @@ int orc_num_candidates(const HmpSampling* sampling, int n_extra) {
 		total *= computeAmplifierSamples(sampling->amp_min[a], sampling->amp_max[a], sampling->amp_granularity[a]).size();
 	}
 	return (int)(total + n_extra);
+}
+
+int orc_build_environment(const HmpEnvParams* env, const double robot_pose[3], const double pose_ref[3], const HmpShape* shapes,
+                          int32_t n_shapes, const double* vertices_xy, int32_t n_vertices, const HmpPerson* people, int32_t n_people,
+                          const HmpGroup* groups, int32_t n_groups, HmpObstacle* obstacles_out, int32_t* n_obstacles_out,
+                          int32_t* people_selected, int32_t* n_people_selected, int32_t* groups_selected, int32_t* n_groups_selected) {
+	(void)n_vertices;
+	EnvModel m = createEnvironmentModel(*env, robot_pose, pose_ref, shapes, n_shapes, vertices_xy, people, n_people, groups, n_groups);
+	if ((int)m.obstacles.size() > *n_obstacles_out) return -1;
+	std::memcpy(obstacles_out, m.obstacles.data(), m.obstacles.size() * sizeof(HmpObstacle));
+	*n_obstacles_out = (int)m.obstacles.size();
+	for (size_t i = 0; i < m.people.size(); ++i) people_selected[i] = m.people[i];
+	*n_people_selected = (int)m.people.size();
+	for (size_t i = 0; i < m.groups.size(); ++i) groups_selected[i] = m.groups[i];
+	*n_groups_selected = (int)m.groups.size();
+	return 0;
+}
+
+// HumapPlanner::computeForceAtPosition (src/humap_planner.cpp:652-678) -> generateTrajectoryWithoutPlanning
+// (social_trajectory_generator.cpp:504-527: computeForces with SampleAmplifierSet() and dt = sim_period_)
+int orc_force_grid(const HmpParams* P, const HmpEnvParams* env, const HmpWorld* hw, const double* positions_xy, int32_t n_positions,
+                   const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy, int32_t n_vertices, double* forces_out) {
+	(void)n_vertices;
+	const double robot_pose[3] = {hw->robot_x, hw->robot_y, hw->robot_yaw};
+	Pose pose_(hw->robot_x, hw->robot_y, hw->robot_yaw);
+	V3 vel_glob = computeVelocityGlobal({hw->vel_x, hw->vel_y, hw->vel_th}, pose_);
+	Pose goal_local(hw->goal_local_x, hw->goal_local_y, hw->goal_local_yaw), goal(hw->goal_x, hw->goal_y, hw->goal_yaw);
+	HmpSample unit;
+	for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a) unit.amp[a] = 1.0;
+	FisEngine fis;
+	for (int i = 0; i < n_positions; ++i) {
+		const double pose_ref[3] = {positions_xy[2 * i], positions_xy[2 * i + 1], hw->robot_yaw};
+		Pose pose(pose_ref[0], pose_ref[1], pose_ref[2]);
+		World world(pose, pose, vel_glob, goal_local, goal);
+		EnvModel m = createEnvironmentModel(*env, robot_pose, pose_ref, shapes, n_shapes, vertices_xy, hw->people, hw->n_people, hw->groups,
+		                                    hw->n_groups);
+		for (const HmpObstacle& o : m.obstacles)
+			world.addObstacle(Pose(o.robot_x, o.robot_y, o.robot_yaw), Pose(o.obj_x, o.obj_y, o.obj_yaw), V3{o.vx, o.vy, o.vth}, o.force_dynamic != 0);
+		StepForces f = computeForces(*P, fis, world, P->general.sim_period, unit);
+		double* o = forces_out + 8 * (size_t)i;
+		o[0] = f.internal.x; o[1] = f.internal.y; o[2] = f.dynamic.x; o[3] = f.dynamic.y;
+		o[4] = f.stat.x; o[5] = f.stat.y; o[6] = f.human.x; o[7] = f.human.y;
+	}
+	return 0;
 }
 
 int orc_equisampled_samples(const HmpParams* P, const HmpWorld* w, const HmpEquisampled* eq, double* out, int cap) {

@@ -58,6 +58,14 @@ int orc_score_trajectory(const OrcPlanInput* in, const double* poses, int n, con
 /* HumapPlanner::computeCellCost for every cell (src/humap_planner.cpp:535-576): cloud6[cy * size_x + cx] = {total, path,
  * goal, layered, alignment, goal_front} floats, valid = 0 where the reference returns false */
 int orc_cost_cloud(const OrcPlanInput* in, float* cloud6, uint8_t* valid);
+/* HumapPlanner::createEnvironmentModel (src/humap_planner.cpp:930-1052); same contract as hmp_build_environment */
+int orc_build_environment(const HmpEnvParams* env, const double robot_pose[3], const double pose_ref[3], const HmpShape* shapes,
+                          int32_t n_shapes, const double* vertices_xy, int32_t n_vertices, const HmpPerson* people, int32_t n_people,
+                          const HmpGroup* groups, int32_t n_groups, HmpObstacle* obstacles_out, int32_t* n_obstacles_out,
+                          int32_t* people_selected, int32_t* n_people_selected, int32_t* groups_selected, int32_t* n_groups_selected);
+/* HumapPlanner::computeForceAtPosition (src/humap_planner.cpp:652-678) per position; same contract as hmp_compute_force_grid */
+int orc_force_grid(const HmpParams* P, const HmpEnvParams* env, const HmpWorld* world, const double* positions_xy, int32_t n_positions,
+                   const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy, int32_t n_vertices, double* forces_out);
 int orc_num_candidates(const HmpSampling* sampling, int n_extra);
 /* velocity samples of the equisampled generator for this cycle: out[n][3] floats stored as doubles; returns n */
 int orc_equisampled_samples(const HmpParams* P, const HmpWorld* w, const HmpEquisampled* eq, double* out, int cap);

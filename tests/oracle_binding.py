@@ -201,6 +201,36 @@ def plan(params: HmpParams, scene: Scene, sampling: HmpSampling, extra=None, ear
     return arrs
 
 
+def build_environment(env, robot_pose, pose_ref, shapes, vertices, people, groups):
+    """orc_build_environment: same return as Planner.build_environment."""
+    from humap_local_planner_b200.capi import _build_environment, HmpEnvParams
+    L = lib()
+    L.orc_build_environment.argtypes = [C.POINTER(HmpEnvParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    L.orc_build_environment.restype = C.c_int
+
+    def check(rc):
+        assert rc == 0
+
+    return _build_environment(L.orc_build_environment, None, check, env, robot_pose, pose_ref, shapes, vertices, people, groups)
+
+
+def force_grid(params: HmpParams, env, world: HmpWorld, positions, shapes, vertices) -> np.ndarray:
+    from humap_local_planner_b200.capi import HmpEnvParams
+    L = lib()
+    L.orc_force_grid.argtypes = [C.POINTER(HmpParams), C.POINTER(HmpEnvParams), C.POINTER(HmpWorld), C.c_void_p, C.c_int32, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    L.orc_force_grid.restype = C.c_int
+    pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 2)
+    verts = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros((pos.shape[0], 8))
+    ns = len(shapes) if shapes is not None else 0
+    assert L.orc_force_grid(C.byref(params), C.byref(env), C.byref(world), _p(pos), pos.shape[0], C.cast(shapes, C.c_void_p) if ns else None,
+                            ns, _p(verts) if verts.size else None, verts.shape[0], _p(out)) == 0
+    return out
+
+
 def cost_cloud(params: HmpParams, scene: Scene, sampling: HmpSampling, impl: str = "oracle"):
     """HumapPlanner::computeCellCost per cell: (cloud [size_y][size_x][6] float32, valid [size_y][size_x] bool)."""
     L = lib() if impl == "oracle" else ref_lib()

@@ -880,3 +880,58 @@ def test_cost_cloud_bit_exact(planner, name, seed, variant):
     assert gv.sum() > 1000 and (~gv).sum() > 1000
     assert np.array_equal(gv, ov)
     assert np.array_equal(g, o)      # integer-valued costs times FP64 scales rounded to float, summed in float: exact
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "next" rows 3 and 4b: environment-model builder and force-field grid on the device
+# ---------------------------------------------------------------------------------------------------------------
+def _obstacle_table(arr, n):
+    return np.array([[o.robot_x, o.robot_y, o.robot_yaw, o.obj_x, o.obj_y, o.obj_yaw, o.vx, o.vy, o.vth, o.force_dynamic]
+                     for o in list(arr)[:n]])
+
+
+@pytest.mark.parametrize("seed,closest,model,pose_ref", [(0, (-1, -1, -1), 1, (0.0, 0.0, 0.0)), (1, (20, 3, 1), 1, (0.6, -0.3, 0.4)),
+                                                        (2, (5, 0, -1), 0, (1.5, 1.0, -2.0)), (3, (0, 2, 0), 1, (-0.4, 0.8, 3.0)),
+                                                        (4, (12, -1, -1), 1, (2.0, 0.1, 0.0))])
+def test_environment_model(planner, seed, closest, model, pose_ref):
+    cfg = scenes.CONFIGS["cfg1"]
+    sc = scenes.make_scene(cfg, seed)
+    people = [sc._people[i] for i in range(sc.world.n_people)]
+    shapes, verts = scenes.make_shapes(seed, 60, people=people)
+    env = scenes.make_env_params(closest=closest, robot_model=model)
+    if seed == 4:
+        env.obstacles_force_dynamic = 1
+        env.obstacle_extension_multiplier = 3.0      # large extension: exercises the fallback stage of enlargeObstacle
+    robot_pose = (0.0, 0.0, 0.0)
+    g_out, g_n, g_ps, g_gs = planner.build_environment(env, robot_pose, pose_ref, shapes, verts, sc._people, sc._groups)
+    o_out, o_n, o_ps, o_gs = ob.build_environment(env, robot_pose, pose_ref, shapes, verts, sc._people, sc._groups)
+    assert g_n == o_n and np.array_equal(g_ps, o_ps) and np.array_equal(g_gs, o_gs)
+    if closest[0] < 0:
+        # the six leg-like obstacles sitting on people are dropped (plus any random one that happens to lie inside a person)
+        assert len(shapes) - 12 + len(g_ps) <= g_n <= len(shapes) - 6 + len(g_ps)
+    gt, ot = _obstacle_table(g_out, g_n), _obstacle_table(o_out, o_n)
+    assert np.array_equal(gt[:, 9], ot[:, 9])
+    assert np.abs(gt - ot).max() < 1e-12
+
+
+@pytest.mark.parametrize("seed,fis", [(0, True), (1, True), (2, False)])
+def test_force_grid(planner, seed, fis):
+    """computeForceAtPosition on the 9 x 9 grid of Visualization::publishGrid (4 m x 4 m, 0.5 m) around the robot."""
+    cfg = scenes.CONFIGS["cfg0"]
+    sc = scenes.make_scene(cfg, seed, base_vel=(0.4, 0.0, 0.1))
+    params = scenes.make_params(cfg, fis=fis)
+    planner.set_params(params)
+    planner.set_scene(sc)
+    people = [sc._people[i] for i in range(sc.world.n_people)]
+    shapes, verts = scenes.make_shapes(seed, 30, people=people)
+    env = scenes.make_env_params(closest=(-1, -1, -1))
+    xs = np.arange(-2.0, 2.0 + 1e-9, 0.5)
+    pos = np.stack(np.meshgrid(sc.world.robot_x + xs, sc.world.robot_y + xs, indexing="ij"), axis=-1).reshape(-1, 2)
+    g = planner.force_grid(env, sc.world, pos, shapes, verts)
+    o = ob.force_grid(params, env, sc.world, pos, shapes, verts)
+    assert g.shape == (81, 8) and np.isfinite(o).all()
+    assert np.abs(o[:, 4:6]).max() > 0.1 and np.abs(o[:, 0:2]).max() > 1.0      # static and internal forces present
+    if fis:
+        assert np.abs(o[:, 6:8]).max() > 1e-3                                     # human-action force present
+    scale = np.maximum(np.abs(o).max(axis=1, keepdims=True), 1.0)
+    assert (np.abs(g - o) / scale).max() < 1e-9
