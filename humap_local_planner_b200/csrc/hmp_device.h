@@ -20,6 +20,9 @@
 #ifndef HMP_LOCKSTEP
 #define HMP_LOCKSTEP 1
 #endif
+#ifndef HMP_LOCKSTEP_PERIOD
+#define HMP_LOCKSTEP_PERIOD 1   /* steps between two block barriers of the lockstep rollout */
+#endif
 #ifndef HMP_LOCKSTEP_EXTRA
 #define HMP_LOCKSTEP_EXTRA 0
 #endif
