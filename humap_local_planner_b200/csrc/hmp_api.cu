@@ -1098,11 +1098,20 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		Rf.totals = r_totals;
 		Rf.d_nposes = r_nposes;
 		Rf.d_forces = nullptr;
-		// few candidates, many SMs: spread them (2 per block for a single scene) to shorten the serial FP64 rollout
-		Rf.warps_per_ticket = (NS == 1) ? 2 : HMP_WARPS_PER_BLOCK;
-		const int wpt = Rf.warps_per_ticket;
-		const int rblocks = (K + wpt - 1) / wpt;
-		CU(hmp_dev_launch_plan(&Rf, rblocks, 1, smem, st));
+		// single scene: few candidates, many SMs -> one candidate per BLOCK (block-cooperative instance), as many blocks as
+		// the GPU holds; batches have enough leaders in total to keep one warp per candidate
+		// The block-cooperative instance finishes a wave of <= sm_count leaders in ~0.85 ms (cfg2), the warp-per-candidate
+		// instance any number up to 2 x sm_count in ~1.4 ms; the count is only known on the device, so the choice follows
+		// the previous cycle's count (consecutive control cycles have similar leader sets).
+		if (NS == 1 && ctx->last_n_leaders <= ctx->sm_count) {
+			CU(hmp_dev_launch_plan(&Rf, std::min(K, ctx->sm_count), 3, smem, st));
+		} else if (NS == 1) {
+			Rf.warps_per_ticket = 2;
+			CU(hmp_dev_launch_plan(&Rf, (K + 1) / 2, 1, smem, st));
+		} else {
+			Rf.warps_per_ticket = HMP_WARPS_PER_BLOCK;
+			CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
+		}
 		CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
 		                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, st));
 		ctx->launches += 3;
