@@ -172,6 +172,8 @@ struct HmpContext {
 	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
 	HostBuf h_seeds[HMP_NUM_MAPGRIDS];
 	cudaEvent_t seeds_event[HMP_NUM_MAPGRIDS] = {nullptr, nullptr, nullptr, nullptr};
+	cudaStream_t wf_stream[HMP_NUM_MAPGRIDS] = {nullptr, nullptr, nullptr, nullptr};   // the four wave fronts of a cycle run side by side
+	cudaEvent_t wf_done[HMP_NUM_MAPGRIDS] = {nullptr, nullptr, nullptr, nullptr};
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
@@ -682,6 +684,14 @@ HmpContext* hmp_create(int device_id) {
 	    cudaEventCreateWithFlags(&ctx->seeds_event[1], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->seeds_event[2], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->seeds_event[3], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->wf_stream[0], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->wf_stream[1], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->wf_stream[2], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->wf_stream[3], cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->wf_done[0], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->wf_done[1], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->wf_done[2], cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->wf_done[3], cudaEventDisableTiming) != cudaSuccess ||
 	    hmp_dev_configure(ctx->max_smem_optin) != cudaSuccess) {
 		set_err("context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
 		delete ctx;
@@ -698,6 +708,11 @@ void hmp_destroy(HmpContext* ctx) {
 		ctx->d_seeds[g].release();
 		ctx->h_seeds[g].release();
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
+		if (ctx->wf_stream[g]) {
+			cudaStreamSynchronize(ctx->wf_stream[g]);
+			cudaStreamDestroy(ctx->wf_stream[g]);
+		}
+		if (ctx->wf_done[g]) cudaEventDestroy(ctx->wf_done[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
 	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env};
@@ -740,6 +755,8 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
 		return HMP_E_CAPACITY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g)   // a wave front still reading the old cells must finish first
+		if (ctx->wavefront_pending[g]) CU(cudaStreamSynchronize(ctx->wf_stream[g]));
 	if (size_x != ctx->size_x || size_y != ctx->size_y) {
 		for (bool& b : ctx->have_grid) b = false;
 	}
@@ -779,6 +796,10 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	if (ctx->wavefront_pending[grid]) {   // an uploaded grid replaces a device wave front still in flight for this slot
+		CU(cudaStreamSynchronize(ctx->wf_stream[grid]));
+		ctx->wavefront_pending[grid] = false;
+	}
 	size_t n = (size_t)ctx->size_x * ctx->size_y;
 	int rc = ctx->h_stage.ensure(n * sizeof(float));
 	if (rc) return rc;
@@ -805,13 +826,21 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 // Checks the overflow flag of queued wave fronts; a grid whose frontier overflowed the shared-memory queues is recomputed
 // with the scan kernel (never observed for 200 x 200 windows; kept for correctness on pathological maps).
 static int resolve_wavefronts(HmpContext* ctx) {
+	// join the side streams of the pending wave fronts, then read their overflow flags with ONE synchronisation
+	int status[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
+	bool any = false;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!ctx->wavefront_pending[g]) continue;
+		CU(cudaStreamWaitEvent(ctx->stream, ctx->wf_done[g], 0));
+		CU(cudaMemcpyAsync(&status[g], ctx->d_seeds[g].p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		any = true;
+	}
+	if (!any) return HMP_OK;
+	CU(cudaStreamSynchronize(ctx->stream));
 	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
 		if (!ctx->wavefront_pending[g]) continue;
 		ctx->wavefront_pending[g] = false;
-		int status = 0;
-		CU(cudaMemcpyAsync(&status, ctx->d_seeds[g].p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-		CU(cudaStreamSynchronize(ctx->stream));
-		if (status) {
+		if (status[g]) {   // frontier queue overflowed: redo this grid with the scan-based kernel
 			const size_t n = (size_t)ctx->size_x * ctx->size_y;
 			CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p, ctx->size_x, ctx->size_y, (const int*)ctx->d_seeds[g].p + 1,
 			                            ctx->n_seeds[g], (float*)ctx->d_mapgrids.p + (size_t)g * n, ctx->stream));
@@ -903,13 +932,16 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 	int* hs = (int*)ctx->h_seeds[grid].p;
 	hs[0] = 0;
 	if (!seeds.empty()) std::memcpy(hs + 1, seeds.data(), seeds.size() * sizeof(int));
-	cudaStream_t st = ctx->stream;
+	// each grid has its own stream: hmp_set_costmap has synchronised (the cells are on the device), the previous plan has
+	// synchronised (nobody reads the MapGrid buffer), so the four single-block wave fronts of a cycle can overlap
+	cudaStream_t st = ctx->wf_stream[grid];
 	int* dsd = (int*)ctx->d_seeds[grid].p;
 	CU(cudaMemcpyAsync(dsd, hs, need, cudaMemcpyHostToDevice, st));
 	CU(cudaEventRecord(ctx->seeds_event[grid], st));
 	ctx->seeds_event_valid[grid] = true;
 	float* out = (float*)ctx->d_mapgrids.p + (size_t)grid * n;
 	CU(hmp_dev_launch_wavefront_queue((const uint8_t*)ctx->d_costmaps.p, sx, sy, dsd + 1, (int)seeds.size(), out, dsd, st));
+	CU(cudaEventRecord(ctx->wf_done[grid], st));
 	ctx->launches++;
 	ctx->wavefront_pending[grid] = true;
 	ctx->n_seeds[grid] = (int)seeds.size();   // overflow status is checked (and the scan kernel re-run) before the next plan
