@@ -935,3 +935,55 @@ def test_force_grid(planner, seed, fis):
         assert np.abs(o[:, 6:8]).max() > 1e-3                                     # human-action force present
     scale = np.maximum(np.abs(o).max(axis=1, keepdims=True), 1.0)
     assert (np.abs(g - o) / scale).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# error behaviour of the C ABI: status codes instead of exceptions / crashes, nothing computed on bad input
+# ---------------------------------------------------------------------------------------------------------------
+def test_error_codes():
+    from humap_local_planner_b200 import Planner
+    from humap_local_planner_b200 import capi
+    cfg = scenes.CONFIGS["cfg0"]
+    sc = scenes.make_scene(cfg, 0)
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    pl = Planner(0)
+
+    def code(fn, *a, **k):
+        try:
+            fn(*a, **k)
+        except capi.HmpError as e:
+            return e.code
+        return 0
+
+    try:
+        assert code(pl.plan, sc.world, smp) == capi.HMP_E_NOT_READY                 # no params
+        pl.set_params(params)
+        assert code(pl.plan, sc.world, smp) == capi.HMP_E_NOT_READY                 # no costmap
+        pl.set_costmap(sc.cells, sc.origin_x, sc.origin_y, sc.resolution)
+        assert code(pl.plan, sc.world, smp) == capi.HMP_E_NOT_READY                 # MapGrids / footprint missing
+        assert code(pl.cost_cloud) == capi.HMP_E_NOT_READY
+        pl.set_scene(sc)
+        assert code(pl.set_footprint, np.zeros((64 + 1, 2))) == capi.HMP_E_CAPACITY
+        bad = scenes.make_params(cfg)
+        bad.general.sim_granularity = 0.0
+        assert code(pl.set_params, bad) == capi.HMP_E_INVALID
+        long_horizon = scenes.make_params(cfg)
+        long_horizon.general.sim_time = 100.0                                          # 1000 steps > HMP_MAX_STEPS
+        pl.set_params(long_horizon)
+        assert code(pl.plan, sc.world, smp) == capi.HMP_E_CAPACITY
+        pl.set_params(params)
+        w = capi.HmpWorld()
+        C.memmove(C.byref(w), C.byref(sc.world), C.sizeof(w))
+        w.n_people = -1
+        assert code(pl.plan, w, smp) == capi.HMP_E_INVALID
+        assert code(pl.set_refinement, -0.1, 16) == capi.HMP_E_INVALID
+        assert code(pl.explored_totals, 5) in (capi.HMP_E_NOT_READY, capi.HMP_E_INVALID)
+        env = scenes.make_env_params(robot_model=2)                                    # two-circle model: not built
+        shapes, verts = scenes.make_shapes(0, 4)
+        assert code(pl.build_environment, env, (0, 0, 0), (0, 0, 0), shapes, verts, None, None) == capi.HMP_E_INVALID
+        # after all of that the context still plans
+        res, _ = pl.plan(sc.world, smp)
+        assert res.n_candidates == 72 and res.best_index >= 0
+    finally:
+        pl.close()
