@@ -418,6 +418,8 @@ def main():
             pass
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         peak_fp32 = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        peak_fp32_measured = pl.measure_fp32_peak()       # FFMA micro-benchmark on this GPU, same launch shape as the sweep
+        hbm_peak = float(peaks.get("hbm_gbs", 0.0)) or None
         line = {
             "metric": METRIC, "value": world * C * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -434,6 +436,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32-cuda-core", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp32, "traffic": traffic,
+                         "peak_measured": peak_fp32_measured, "frac_of_measured": achieved / peak_fp32_measured,
+                         "hbm": {"achieved_gbs": (traffic / sel_s / 1e9) if traffic else None, "peak_gbs": hbm_peak},
                          "note": f"algorithmic flop per candidate-step W={W} (SURVEY.md 8d formula), per candidate T*W+60; dominant kernel "
                                  f"plan_kernel<false,float> avg {1e3 * sel_s:.3f} ms; peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz "
                                  "(MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is not HBM- or tensor-bound)"},

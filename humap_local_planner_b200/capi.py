@@ -142,7 +142,7 @@ ABI_SYMBOLS = (
     "hmp_set_mapgrid", "hmp_set_footprint", "hmp_plan", "hmp_plan_batch", "hmp_replan_resident",
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
-    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid",
+    "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -203,6 +203,8 @@ def load_library() -> C.CDLL:
     lib.hmp_compute_force_grid.argtypes = [C.c_void_p, P(HmpEnvParams), P(HmpWorld), C.c_void_p, _i, C.c_void_p, _i, C.c_void_p, _i,
                                            C.c_void_p]
     lib.hmp_compute_force_grid.restype = C.c_int
+    lib.hmp_debug_measure_fp32_peak.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmp_debug_measure_fp32_peak.restype = C.c_int
     lib.hmp_compute_cost_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hmp_compute_cost_cloud.restype = C.c_int
     lib.hmp_last_num_leaders.argtypes = [C.c_void_p]
@@ -330,6 +332,12 @@ class Planner:
                                                      C.cast(shapes, C.c_void_p) if ns else None, ns,
                                                      _ptr(verts) if verts.size else None, verts.shape[0], _ptr(out)))
         return out
+
+    def measure_fp32_peak(self) -> float:
+        """Measured FP32 FFMA throughput of this GPU in TFLOP/s (independent FMA chains, 2 x 256 threads per SM)."""
+        out = C.c_double(0.0)
+        self._check(self._lib.hmp_debug_measure_fp32_peak(self._ctx, C.byref(out)))
+        return float(out.value)
 
     def last_num_leaders(self) -> int:
         return int(self._lib.hmp_last_num_leaders(self._ctx))

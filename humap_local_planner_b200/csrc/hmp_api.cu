@@ -54,6 +54,7 @@ extern "C" cudaError_t hmp_dev_launch_wavefront(const uint8_t* cm, int sx, int s
 extern "C" cudaError_t hmp_dev_launch_wavefront_queue(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
                                                       int* status, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_ffma_peak(int blocks, int iters, float* sink, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_cost_cloud(const DevParams* P, int n_cells, const uint8_t* cm, const float* mapgrids, const double* hv,
                                                  float* out, uint8_t* valid, cudaStream_t stream);
 
@@ -1810,6 +1811,34 @@ int hmp_compute_force_grid(HmpContext* ctx, const HmpEnvParams* env, const HmpWo
 	CU(cudaMemcpyAsync(forces_out, ctx->d_dbg.p, f_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+// Measured FP32 FFMA throughput of this device at the main sweep's launch shape (2 x 256 threads per SM): the denominator of
+// bench.py's roofline next to the nominal SMs x 128 lanes x 2 x clock. Best of 5 timed launches of ~2 ms.
+int hmp_debug_measure_fp32_peak(HmpContext* ctx, double* tflops_out) {
+	if (!ctx || !tflops_out) {
+		set_err("bad arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	int rc = ctx->d_dbg.ensure(64);
+	if (rc) return rc;
+	const int blocks = ctx->sm_count * 2, iters = 1 << 16;
+	cudaStream_t st = ctx->stream;
+	CU(hmp_dev_launch_ffma_peak(blocks, iters, (float*)ctx->d_dbg.p, st));   // warm-up
+	double best_ms = 1e30;
+	for (int k = 0; k < 5; ++k) {
+		CU(cudaEventRecord(ctx->ev0, st));
+		CU(hmp_dev_launch_ffma_peak(blocks, iters, (float*)ctx->d_dbg.p, st));
+		CU(cudaEventRecord(ctx->ev1, st));
+		CU(cudaStreamSynchronize(st));
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		best_ms = std::min(best_ms, (double)ms);
+		ctx->launches++;
+	}
+	*tflops_out = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0 / (best_ms * 1e-3) / 1e12;
 	return HMP_OK;
 }
 

@@ -15,7 +15,9 @@
 #include "../../include/hmp_planner.h"
 
 #define HMP_DEV_MAX_KERNEL_PTS 9   /* centre + 8 offsets (RECTANGLE kernel) */
+#ifndef HMP_WARPS_PER_BLOCK
 #define HMP_WARPS_PER_BLOCK 8
+#endif
 #define HMP_THREADS_PER_BLOCK (32 * HMP_WARPS_PER_BLOCK)
 #ifndef HMP_LOCKSTEP
 #define HMP_LOCKSTEP 1

@@ -429,6 +429,9 @@ int hmp_debug_fis(HmpContext* ctx, const double* in4, int32_t n, double* out2);
 /* Per-step forces of the candidates of the last hmp_explain call: [n][T][8] doubles
  * (internal.xy, dynamic.xy, static.xy, human-action.xy), social_trajectory_generator.cpp:701-704. */
 int hmp_debug_last_forces(HmpContext* ctx, int32_t n, double* forces_out);
+/* FP32 FFMA throughput of the device measured with independent FMA chains at the main sweep's launch shape (TFLOP/s): the
+ * measured denominator of the roofline fraction bench.py reports beside the nominal one. */
+int hmp_debug_measure_fp32_peak(HmpContext* ctx, double* tflops_out);
 /* Rollout steps of the last plan (SocialTrajectoryGenerator::computeStepsNumber), -1 if none. */
 int hmp_num_steps(HmpContext* ctx);
 
