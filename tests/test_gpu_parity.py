@@ -987,3 +987,29 @@ def test_error_codes():
         assert res.n_candidates == 72 and res.best_index >= 0
     finally:
         pl.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# maps that do not fit shared memory (costmap read through L1 / L2) and a finer resolution
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size,res", [(480, 0.025), (640, 0.05)])
+def test_large_costmap_global_memory_path(planner, size, res):
+    from humap_local_planner_b200.scenes import CycleConfig
+    cfg = CycleConfig("big", 4, 1, 30, 3.5, 0.1, config.SAMPLING_CFG_DEFAULT, size=size, resolution=res)
+    sc = scenes.make_scene(cfg, 3)
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    planner.set_precision(1)
+    planner.set_params(params)
+    planner.set_scene(sc)
+    res_, poses = planner.plan(sc.world, smp)
+    g = planner.explored_totals(res_.n_candidates)
+    planner.set_precision(False)
+    o = ob.plan(params, sc, smp)
+    assert res_.n_candidates == o["C"] == 72
+    assert np.array_equal(g < 0, o["totals"] < 0) and np.array_equal(g[g < 0], o["totals"][g < 0])
+    v = g >= 0
+    assert v.sum() >= 10
+    assert np.abs(g[v] - o["totals"][v]).max() <= 1e-6 * np.abs(o["totals"][v]).max()
+    assert res_.best_index == o["result"].best_index
+    assert np.abs(poses - o["poses"][res_.best_index]).max() < 1e-8
