@@ -308,9 +308,12 @@ def main():
         return
 
     cfg = scenes.CONFIGS[args.cfg]
-    # independent scenes are sharded over ranks (scene s -> rank s mod N), one scene per rank per step: weak scaling
+    # independent scenes are sharded over ranks (scene s -> rank s mod N), one scene per rank per step: weak scaling. Every
+    # rank plans its own copy of the SAME synthetic world (seed 0), so that the work per GPU is identical at every N (the
+    # cost of a cycle varies by ~10 % between seeds, which would otherwise show up as a scaling loss through the max over ranks)
     my_scene_ids = scenes_for_rank(world, rank, world)
-    scene = scenes.make_scene(cfg, seed=my_scene_ids[0])
+    assert my_scene_ids == [rank]
+    scene = scenes.make_scene(cfg, seed=0)
     params = scenes.make_params(cfg, fis=bool(args.fis))
     sampling = scenes.make_sampling(cfg)
     pl = Planner(local_rank)
@@ -425,7 +428,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {0: "f32", 1: "f64", 2: "f32 sweep + f64 refinement of the leaders"}[int(args.precise)], "data": "synthetic",
             "config": {"workload": _workload_name(cfg, args), "candidates": C, "steps_per_rollout": T,
-                       "parallelism": f"independent scenes x{world}, one per rank, no collective",
+                       "parallelism": f"independent scenes x{world} (copies of the seed-0 world), one per rank, no collective",
                        "l2": "flushed with a 256 MiB write between timed iterations", "timing": "CUDA events on the launching stream"},
             "p50_cycle_ms": statistics.median(dev_ms), "p99_cycle_ms": sorted(dev_ms)[min(len(dev_ms) - 1, int(0.99 * len(dev_ms)))],
             "p50_cycle_ms_e2e": 1e3 * statistics.median(e2e_times),
