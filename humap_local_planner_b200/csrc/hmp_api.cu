@@ -180,6 +180,7 @@ struct HmpContext {
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env;
 	HostBuf h_stage, h_out;
+	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
 
 	// last plan
@@ -708,6 +709,7 @@ void hmp_destroy(HmpContext* ctx) {
 	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
 		ctx->d_seeds[g].release();
 		ctx->h_seeds[g].release();
+		ctx->h_grid[g].release();
 		if (ctx->seeds_event[g]) cudaEventDestroy(ctx->seeds_event[g]);
 		if (ctx->wf_stream[g]) {
 			cudaStreamSynchronize(ctx->wf_stream[g]);
@@ -802,21 +804,31 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 		ctx->wavefront_pending[grid] = false;
 	}
 	size_t n = (size_t)ctx->size_x * ctx->size_y;
-	int rc = ctx->h_stage.ensure(n * sizeof(float));
+	// one pinned staging buffer per slot: the four uploads of a cycle queue on the stream without a host synchronisation
+	// (the previous cycle's plan has synchronised, so the buffer is free); the conversion loop is branch-free so that the
+	// host compiler vectorises it (it used to be a third of the e2e overhead of a cycle)
+	if (n * sizeof(float) > ctx->h_grid[grid].cap) CU(cudaStreamSynchronize(ctx->stream));
+	int rc = ctx->h_grid[grid].ensure(n * sizeof(float));
 	if (rc) return rc;
-	CU(cudaStreamSynchronize(ctx->stream));
-	float* f = (float*)ctx->h_stage.p;
+	float* f = (float*)ctx->h_grid[grid].p;
 	const double limit = (double)n + 1.0;
+	int bad = 0;
 	for (size_t i = 0; i < n; ++i) {
-		double v = target_dist[i];
-		if (!(v >= 0.0) || v > limit || v != std::floor(v)) {
-			set_err("target_dist[%zu] = %g is not a cell count in [0, size_x*size_y+1]", i, v);
-			return HMP_E_INVALID;
+		const double v = target_dist[i];
+		const int iv = (int)v;   // NaN / out-of-range convert to INT_MIN on x86-64 and fail the round trip below
+		bad |= ((double)iv != v) | (iv < 0) | (v > limit);
+		f[i] = (float)iv;
+	}
+	if (bad) {
+		for (size_t i = 0; i < n; ++i) {
+			const double v = target_dist[i];
+			if (!(v >= 0.0) || v > limit || v != std::floor(v)) {
+				set_err("target_dist[%zu] = %g is not a cell count in [0, size_x*size_y+1]", i, v);
+				return HMP_E_INVALID;
+			}
 		}
-		f[i] = (float)v;
 	}
 	CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + (size_t)grid * n, f, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
 	ctx->have_grid[grid] = true;
 	ctx->hv_prev[grid] = highest_valid_cost_prev;
 	ctx->last_valid = false;
