@@ -209,6 +209,7 @@ def run_batched(args, rank, local_rank, world, barrier):
     sampling = scenes.make_sampling(cfg)
     pl = Planner(local_rank)
     pl.set_precision(int(args.precise))
+    pl.set_sweep_layout(int(args.layout))
     pl.set_params(params)
     pl.set_scene(first)
     n_local = len(mine)
@@ -275,6 +276,7 @@ def main():
                     help="batched-scenes mode (BASELINE config 4, use with --cfg cfg3): this many independent worlds in total, "
                          "sharded over the ranks, one hmp_plan_batch launch per rank per step; 0 = single-scene mode")
     ap.add_argument("--precise", type=int, default=2, help="hmp_set_precision mode: 0 FP32 object loops, 1 FP64 (exact-parity mode), 2 FP32 sweep + FP64 refinement of the leaders")
+    ap.add_argument("--layout", type=int, default=0, help="hmp_set_sweep_layout: 0 automatic, 1 one warp per candidate, 2 one thread per candidate")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -318,6 +320,7 @@ def main():
     sampling = scenes.make_sampling(cfg)
     pl = Planner(local_rank)
     pl.set_precision(int(args.precise))
+    pl.set_sweep_layout(int(args.layout))
     pl.set_params(params)
 
     def full_cycle():
@@ -405,6 +408,9 @@ def main():
         flops_cand, W = algorithmic_flops_per_candidate(cfg, params, ns, nd, bool(args.fis), T)
         sel_s = statistics.mean(sel_ms) * 1e-3
         achieved = C * flops_cand / sel_s / 1e12
+        mode = pl.last_sweep_mode()
+        sweep_name = (f"sweep_tpc_kernel (one thread per candidate, {mode} threads per block)" if mode
+                      else "plan_kernel<false,float> (one warp per candidate)")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -442,7 +448,7 @@ def main():
                          "peak_measured": peak_fp32_measured, "frac_of_measured": achieved / peak_fp32_measured,
                          "hbm": {"achieved_gbs": (traffic / sel_s / 1e9) if traffic else None, "peak_gbs": hbm_peak},
                          "note": f"algorithmic flop per candidate-step W={W} (SURVEY.md 8d formula), per candidate T*W+60; dominant kernel "
-                                 f"plan_kernel<false,float> avg {1e3 * sel_s:.3f} ms; peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz "
+                                 f"{sweep_name} avg {1e3 * sel_s:.3f} ms; peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz "
                                  "(MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is not HBM- or tensor-bound)"},
             "best_index": int(r.best_index), "best_total": float(r.best_total), "n_valid": int(r.n_valid),
         }

@@ -32,7 +32,7 @@ def _stale(target: str, sources) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, "hmp_kernels.cu"), os.path.join(CSRC, "hmp_api.cu")]
-    deps = srcs + [os.path.join(CSRC, "hmp_device.h"), os.path.join(HERE, "..", "include", "hmp_planner.h")]
+    deps = srcs + [os.path.join(CSRC, "hmp_device.h"), os.path.join(CSRC, "hmp_sweep_tpc.inl"), os.path.join(HERE, "..", "include", "hmp_planner.h")]
     if force or _stale(LIB, deps):
         os.makedirs(LIB_DIR, exist_ok=True)
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs

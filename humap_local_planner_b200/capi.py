@@ -143,6 +143,7 @@ ABI_SYMBOLS = (
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
     "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
+    "hmp_set_sweep_layout", "hmp_last_sweep_mode",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -193,6 +194,10 @@ def load_library() -> C.CDLL:
     lib.hmp_get_mapgrid.restype = C.c_int
     lib.hmp_set_precision.restype = C.c_int
     lib.hmp_set_refinement.argtypes = [C.c_void_p, _d, _i]
+    lib.hmp_set_sweep_layout.argtypes = [C.c_void_p, _i]
+    lib.hmp_set_sweep_layout.restype = C.c_int
+    lib.hmp_last_sweep_mode.argtypes = [C.c_void_p]
+    lib.hmp_last_sweep_mode.restype = C.c_int
     lib.hmp_set_refinement.restype = C.c_int
     lib.hmp_set_equisampled.argtypes = [C.c_void_p, C.c_void_p]
     lib.hmp_set_equisampled.restype = C.c_int
@@ -303,6 +308,14 @@ class Planner:
 
     def set_refinement(self, rel_window: float = 0.02, max_leaders: int = 256):
         self._check(self._lib.hmp_set_refinement(self._ctx, float(rel_window), int(max_leaders)))
+
+    def set_sweep_layout(self, layout: int = 0):
+        """FP32 sweep: 0 automatic, 1 one warp per candidate, 2 one thread per candidate."""
+        self._check(self._lib.hmp_set_sweep_layout(self._ctx, int(layout)))
+
+    def last_sweep_mode(self) -> int:
+        """0 = the last main sweep ran one warp per candidate, else the block size of the thread-per-candidate kernel."""
+        return int(self._lib.hmp_last_sweep_mode(self._ctx))
 
     def set_equisampled(self, eq: Optional["HmpEquisampled"]):
         """Second generator of the pool (equisampled velocities); None turns it off."""

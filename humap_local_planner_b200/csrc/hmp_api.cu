@@ -29,6 +29,8 @@ static_assert(sizeof(DevDynamic) == 64 && sizeof(DevPerson) == 64 && sizeof(DevG
 extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_stride, int costmap_in_smem);
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
+extern "C" cudaError_t hmp_dev_occupancy_tpc(size_t smem, int threads, int* blocks_per_sm);
+extern "C" int hmp_dev_tpc_max_threads();
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_env_filter(const HmpShape* shapes, int n_shapes, const double* verts, const HmpPerson* people, int n_people,
                                                  double person_radius, double containment_rate, double rx, double ry, int32_t* keep,
@@ -169,6 +171,8 @@ struct HmpContext {
 	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
 	int dilated_scenes = 0;
 	int prune_obstacle = 1;          // HMP_NO_PRUNE=1 in the environment disables the dilated-map pruning (A/B timing)
+	int sweep_layout = 0;            // FP32 sweep: 0 auto, 1 one warp per candidate, 2 one thread per candidate (hmp_set_sweep_layout)
+	int last_sweep_mode = 0;         // launch mode of the last main sweep (0 warp per candidate, else threads per block of the thread-per-candidate kernel)
 
 	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
 	HostBuf h_seeds[HMP_NUM_MAPGRIDS];
@@ -597,7 +601,7 @@ struct PlanLaunch {
 };
 
 int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* blocks_x_out, size_t* smem_out,
-                int* costmap_in_smem_out) {
+                int* costmap_in_smem_out, int* sweep_mode_out = nullptr) {
 	const int C = D.n_social;
 	size_t cm_bytes = (size_t)ctx->costmap_stride;
 	int in_smem = 1;
@@ -610,15 +614,30 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 			return HMP_E_CAPACITY;
 		}
 	}
+	// Layout of the FP32 sweep. One warp per candidate (plan_kernel) has the shortest latency for a few thousand
+	// candidates; one thread per candidate (sweep_tpc_kernel) issues the per-step scalar section once per 32 candidates
+	// and wins as soon as the launch holds enough candidates to give every SM sub-partition a warp.
+	int tpc_threads = 0;
+	if (sweep_mode_out && ctx->precise != 1) {
+		const long long total = (long long)C * pl.n_scenes;
+		const bool want = ctx->sweep_layout == 2 || (ctx->sweep_layout == 0 && total >= 16384);
+		if (want) {
+			tpc_threads = hmp_dev_tpc_max_threads();
+			// few candidates: smaller blocks so that every SM gets one
+			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes < ctx->sm_count) tpc_threads /= 2;
+		}
+	}
 	int bps = 0;
-	CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
+	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem, tpc_threads, &bps));
+	else CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
 		return HMP_E_CUDA;
 	}
 	// persistent blocks: fill the GPU once; with many scenes give each scene fewer blocks
 	long long resident = (long long)ctx->sm_count * bps;
-	long long need = ((long long)C + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK;
+	const long long per_block = tpc_threads ? tpc_threads : HMP_WARPS_PER_BLOCK;   // candidates a block takes per ticket
+	long long need = ((long long)C + per_block - 1) / per_block;
 	// blocks per scene: one scene fills the GPU once; with several scenes per launch pick the split p that minimises the
 	// number of block waves times the work per block, ceil(n_scenes * p / resident) / p (ties: the finer split)
 	long long per_scene = std::max<long long>(1, std::min<long long>(need, resident));
@@ -632,7 +651,8 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 			}
 		}
 	}
-	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes\n", smem, bps, per_scene, pl.n_scenes);
+	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes, sweep mode %d\n", smem, bps, per_scene, pl.n_scenes, tpc_threads);
+	if (sweep_mode_out) *sweep_mode_out = tpc_threads;
 	*blocks_x_out = (int)per_scene;
 	*smem_out = smem;
 	*costmap_in_smem_out = in_smem;
@@ -678,6 +698,7 @@ HmpContext* hmp_create(int device_id) {
 	}
 	ctx->device = device_id;
 	ctx->prune_obstacle = getenv("HMP_NO_PRUNE") ? 0 : 1;
+	if (const char* e = getenv("HMP_SWEEP_LAYOUT")) ctx->sweep_layout = std::max(0, std::min(2, atoi(e)));
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1029,9 +1050,10 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	if ((rc = ctx->d_detail.ensure(det_bytes))) return rc;
 	if ((rc = ctx->h_out.ensure(det_bytes + cl.total))) return rc;
 
-	int blocks_x = 0, in_smem = 0;
+	int blocks_x = 0, in_smem = 0, sweep_mode = 0;
 	size_t smem = 0;
-	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem))) return rc;
+	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem, &sweep_mode))) return rc;
+	ctx->last_sweep_mode = sweep_mode;
 	if ((rc = ctx->d_block_best.ensure((size_t)NS * blocks_x * 2 * sizeof(unsigned long long)))) return rc;
 
 	cudaStream_t st = ctx->stream;
@@ -1093,7 +1115,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
 		A.best_init = E.best_out;
 	}
-	CU(hmp_dev_launch_plan(&A, blocks_x, 0, smem, st));
+	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem, st));
 	ctx->launches++;
 	CU(cudaEventRecord(ctx->evm, st));
 	// snapshot the counters (n_generated, n_valid) before the detail pass reuses the work ticket
@@ -1888,6 +1910,17 @@ int hmp_set_precision(HmpContext* ctx, int32_t fp64) {
 	ctx->last_valid = false;
 	return HMP_OK;
 }
+
+int hmp_set_sweep_layout(HmpContext* ctx, int32_t layout) {
+	if (!ctx || layout < 0 || layout > 2) {
+		set_err("bad sweep layout (0 auto, 1 warp per candidate, 2 thread per candidate)");
+		return HMP_E_INVALID;
+	}
+	ctx->sweep_layout = layout;
+	return HMP_OK;
+}
+
+int hmp_last_sweep_mode(HmpContext* ctx) { return ctx ? ctx->last_sweep_mode : -1; }
 
 int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq) {
 	if (!ctx) {

@@ -1,0 +1,726 @@
+/*
+ * hmp_sweep_tpc.inl -- the FP32 sweep with one THREAD per candidate (included by hmp_kernels.cu inside namespace hmp).
+ *
+ * plan_kernel gives a candidate a whole warp: the 32 lanes stride over the objects and every lane repeats the per-step
+ * scalar section (internal force, twist, saturation, limits, feasibility, MapGrid look-ups, smoothness sums, pose
+ * integration) and the shuffle reductions. That is the right shape for few candidates (latency of one rollout) but at
+ * 16k+ candidates per scene the redundant scalar work and the partly filled object iterations (50 dynamic objects in
+ * 2 x 32 slots) are about half of all issued instructions. Here a warp rolls out 32 candidates at once: every lane owns
+ * one candidate and walks ALL objects itself; the object records are read with warp-uniform shared-memory loads
+ * (broadcast, no bank conflicts), nothing is reduced across lanes during the rollout, and the scalar section is issued
+ * once per 32 candidates. The arithmetic (FP32 object loops and scalar section, FP64 pose and cell indexing) is the one of
+ * plan_kernel<false, float, false>; only the summation order of the forces differs (sequential instead of lane-strided).
+ *
+ * The one cooperative part is the obstacle critic: a pose whose dilated-map look-up says the footprint must be rasterised
+ * is broadcast to the warp and walked by all 32 lanes with footprint_pose(), pose after pose.
+ *
+ * Reference statements: the same as plan_kernel (file header of hmp_kernels.cu).
+ */
+#ifndef HMP_TPC_THREADS
+#define HMP_TPC_THREADS 256
+#endif
+#ifndef HMP_TPC_UNROLL
+#define HMP_TPC_UNROLL 2
+#endif
+
+__global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_tpc_kernel(const KernelArgs A) {
+	using R = float;
+	using SC = float;
+	using TwistS = TwistT<float>;
+	constexpr int NW = HMP_TPC_THREADS / 32;
+	constexpr int TPC_UNROLL = HMP_TPC_UNROLL;   // static objects in flight per thread
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ uint64_t s_bar;
+	__shared__ double s_wbest[NW];
+	__shared__ int s_widx[NW];
+	__shared__ unsigned int s_hv[HMP_NUM_MAPGRIDS];
+	__shared__ unsigned int s_cnt[2];
+	__shared__ bool s_last;
+	__shared__ int s_base;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+	const int scene = blockIdx.y;
+	const SmemLayout L = smem_layout(A.scene_stride, A.costmap_stride, A.costmap_in_smem);
+
+	// ---- stage parameters + scene blob + costmap window with bulk TMA copies -----------------------
+	if (tid == 0) {
+		mbar_init(&s_bar, 1);
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) s_hv[g] = 0u;
+		s_cnt[0] = s_cnt[1] = 0u;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t bytes = (uint32_t)sizeof(DevParams) + A.scene_stride + (A.costmap_in_smem ? A.costmap_stride : 0u);
+		mbar_expect_tx(&s_bar, bytes);
+		tma_bulk_g2s(smem + L.off_params, A.params, (uint32_t)sizeof(DevParams), &s_bar);
+		tma_bulk_g2s(smem + L.off_scene, A.scenes + (size_t)scene * A.scene_stride, A.scene_stride, &s_bar);
+		if (A.costmap_in_smem)
+			tma_bulk_g2s(smem + L.off_costmap, A.costmaps + (size_t)scene * A.costmap_stride, A.costmap_stride, &s_bar);
+	}
+	mbar_wait(&s_bar, 0);
+
+	const DevParams& P = *reinterpret_cast<const DevParams*>(smem + L.off_params);
+	const unsigned char* blob = smem + L.off_scene;
+	const DevScene& S = *reinterpret_cast<const DevScene*>(blob);
+	const DevStatic* statics = reinterpret_cast<const DevStatic*>(blob + S.off_static);
+	const DevDynamic* dynamics = reinterpret_cast<const DevDynamic*>(blob + S.off_dynamic);
+	const DevPerson* people = reinterpret_cast<const DevPerson*>(blob + S.off_people);
+	const DevGroup* groups = reinterpret_cast<const DevGroup*>(blob + S.off_groups);
+	const uint8_t* cm = A.costmap_in_smem ? (const uint8_t*)(smem + L.off_costmap)
+	                                      : (A.costmaps + (size_t)scene * A.costmap_stride);
+	const uint8_t* dil = A.dilated ? (A.dilated + (size_t)scene * A.costmap_stride) : nullptr;
+	const size_t grid_cells = (size_t)P.size_x * P.size_y;
+	const float* mapgrids = A.mapgrids + (size_t)scene * HMP_NUM_MAPGRIDS * grid_cells;
+	MapGeom G;
+	G.ox = P.origin_x;
+	G.oy = P.origin_y;
+	G.res = P.resolution;
+	G.inv_res = P.inv_resolution;
+	G.sx = P.size_x;
+	G.sy = P.size_y;
+
+	const int T = P.T;
+	const float dt = P.dt;
+	const int n_vel = (T == 1) ? 1 : T - 1;  // velocities of the wrapped Trajectory, trajectory.h:43-103
+	const float obstacle_costs = (float)grid_cells;            // MapGrid::obstacleCosts()
+	const float unreachable_costs = (float)grid_cells + 1.0f;  // MapGrid::unreachableCellCosts()
+	const bool ob_on = P.scale[HMP_COST_OBSTACLE] != 0.0;
+
+	unsigned int* counters = A.counters + (size_t)scene * 4;
+	double tbest = -1.0;   // best of the candidates this thread has scored
+	int tbest_idx = -1;
+	unsigned int n_generated = 0, n_valid = 0;
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_base = (int)atomicAdd(&counters[0], blockDim.x);   // a block may be launched with fewer than HMP_TPC_THREADS threads
+		__syncthreads();
+		if (s_base >= A.n_work) break;
+		const int wk = s_base + tid;
+		const bool active = wk < A.n_work;
+		const int cand = active ? wk + A.cand_offset : 0;
+
+		// ---- SampleAmplifierSet of this candidate (social_trajectory_generator.cpp:166-217) ----------
+		float v_des, An, Bn, Cn, Ap, Bp, Cp, Aw, Bw, As;
+		{
+			double amp[HMP_NUM_AMPLIFIERS];
+			if (cand < P.n_grid) {
+				int rem = cand;
+#pragma unroll
+				for (int a = HMP_NUM_AMPLIFIERS - 1; a >= 0; --a) {
+					int n = P.amp_n[a];
+					int q = rem / n;
+					amp[a] = __ldg(&A.amp_values[a * HMP_MAX_AMP_VALUES + (rem - q * n)]);
+					rem = q;
+				}
+			} else {
+#pragma unroll
+				for (int a = 0; a < HMP_NUM_AMPLIFIERS; ++a)
+					amp[a] = __ldg(&A.extra_samples[(size_t)(cand - P.n_grid) * HMP_NUM_AMPLIFIERS + a]);
+			}
+			// float members of SocialForceModel, social_force_model.h:422-446
+			v_des = (float)((double)P.base[0] * amp[HMP_AMP_SPEED]);
+			An = (float)((double)P.base[1] * amp[HMP_AMP_AN]);
+			Bn = (float)((double)P.base[2] * amp[HMP_AMP_BN]);
+			Cn = (float)((double)P.base[3] * amp[HMP_AMP_CN]);
+			Ap = (float)((double)P.base[4] * amp[HMP_AMP_AP]);
+			Bp = (float)((double)P.base[5] * amp[HMP_AMP_BP]);
+			Cp = (float)((double)P.base[6] * amp[HMP_AMP_CP]);
+			Aw = (float)((double)P.base[7] * amp[HMP_AMP_AW]);
+			Bw = (float)((double)P.base[8] * amp[HMP_AMP_BW]);
+			As = (float)amp[HMP_AMP_AS];
+		}
+
+		// ---- rollout state (per thread = per candidate) ------------------------------------------------
+		double x = S.x0, y = S.y0, th = S.yaw0;   // the pose is FP64 in every instance
+		SC ux = (SC)S.u0x_d, uy = (SC)S.u0y_d, uw = (SC)S.u0w_d;
+		bool rejected = false;
+		float seed_x = 0.f, seed_w = 0.f;
+		bool ob_neg = false;
+		int ob_best = 0;
+		float ob_sum = 0.0f;
+		float mg_last[HMP_NUM_MAPGRIDS], mg_hv[HMP_NUM_MAPGRIDS];
+		int mg_codes = 0;   // 8 bits per grid: 0 ok, else -code
+#pragma unroll
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) mg_last[g] = mg_hv[g] = 0.0f;
+		float ttc_min = CUDART_INF_F;
+		int ttc_first = 0x7fffffff;
+		float hd_max = -CUDART_INF_F, psi_max = -CUDART_INF_F, ps_max = -CUDART_INF_F, fsi_max = -CUDART_INF_F;
+		float un_x = 0.f, un_y = 0.f, un_xy = 0.f;
+		int un_n = 0;
+		float hcs = 0.f, vsm_x = 0.f, vsm_y = 0.f;
+		TwistS prev_tw = {0, 0, 0};
+		float last_tgx = 0.f, last_tgy = 0.f;  // global velocity of the last wrapped-Trajectory velocity (TTC look-ahead)
+
+		const bool forces_on = !P.disable_interaction;
+		const R fovh = (R)P.fov_half_d, fovg = (R)P.fov_gauss_scale_d, fovn = (R)P.fov_neg_inv_2var_d;
+		const R neg_inv_Bw = -1.0f / Bw;
+		const R nbw_l2 = neg_inv_Bw * 1.4426950408889634f, fovn_l2 = fovn * 1.4426950408889634f;
+		const R aw_g = Aw * fovg;
+
+		for (int i = 0; i < T; ++i) {
+			bool alive = active && !rejected;
+			if (!__any_sync(0xffffffffu, alive)) break;   // warp-uniform
+			double cd = 1.0, sd = 0.0;
+			TwistS tw = {0, 0, 0};
+			SC tgx_d = 0, tgy_d = 0;
+			if (alive) {
+				sincos(th, &sd, &cd);
+				const double rxd = x - S.x0, ryd = y - S.y0;
+				const double dpsi = th - S.yaw0;
+				const double tnow = (double)i * P.dt_d;
+				// -- derived robot data (world.cpp:20-33) --
+				const SC speed_d = sqrt_s(ux * ux + uy * uy);
+				const R heading_r = (speed_d <= (SC)0.01) ? (R)th : atan2_r((R)uy, (R)ux);
+				// -- internal force (social_force_model.cpp:311-334) --
+				SC fix, fiy;
+				{
+					SC dx = (SC)(S.glx_d - rxd), dy = (SC)(S.gly_d - ryd);
+					SC dl = sqrt_s(dx * dx + dy * dy);
+					SC inv = (dl <= (SC)1e-6) ? (SC)1 : (SC)1 / dl;
+					fix = (SC)P.m_over_tau * (v_des * (dx * inv) - ux);
+					fiy = (SC)P.m_over_tau * (v_des * (dy * inv) - uy);
+				}
+				const SC gdx = (SC)(S.gx_d - rxd), gdy = (SC)(S.gy_d - ryd);
+				const SC goal_dist = sqrt_s(gdx * gdx + gdy * gdy);
+
+				R fsx = 0, fsy = 0, fhx = 0, fhy = 0, fdx_r = 0, fdy_r = 0;
+				float dmin = CUDART_INF_F;
+				const R c_r = (R)cd, s_r = (R)sd, th_r = (R)th;
+				// -- static objects (social_force_model.cpp:440-514): every object, this candidate --
+				{
+					const int ns = (i == 0) ? S.n_static0 : S.n_static;
+					const R yx = ux * (R)P.dt_d, yy = uy * (R)P.dt_d;
+					const R yl2 = yx * yx + yy * yy;
+					auto static_body = [&](auto gaussian_tag, int j) {
+						constexpr bool GAUSS = decltype(gaussian_tag)::value;
+						const double2 o = reinterpret_cast<const double2*>(statics)[j];   // warp-uniform address: broadcast
+						R dx = (R)(o.x - rxd), dy = (R)(o.y - ryd);
+						R dist, ia;
+						len_inv(dx * dx + dy * dy, dist, ia);
+						dmin = fminf(dmin, dist);
+						R bx = -dx - yx, by = -dy - yy;
+						R bl, ib;
+						len_inv(bx * bx + by * by, bl, ib);
+						R sum = dist + bl;
+						R w = (R)0.5 * sqrt_nr(sum * sum - yl2);
+						const bool valid = forces_on && (fabsf(w) >= (R)1e-8) && !(dist < (R)1e-8);  // false for NaN too
+						if (dist <= (R)1e-6) ia = (R)1;   // ignition Vector3::Normalize leaves near-zero vectors unscaled
+						if (bl <= (R)1e-6) ib = (R)1;
+						R ex = -dx * ia + bx * ib, ey = -dy * ia + by * ib;
+						R arel = wrapf(atan2_r(dy, dx) - heading_r);
+						R gmag;
+						if constexpr (GAUSS) {
+							// Aw e^{-w/Bw} * g e^{-a^2 / (2 sigma^2)} with ONE exponential: both exponents pre-scaled by log2(e)
+							gmag = aw_g * ex2_ftz(fmaf(w, nbw_l2, arel * arel * fovn_l2)) * (sum * w) * (R)0.25;
+						} else {
+							gmag = Aw * expf(w * neg_inv_Bw) * ((sum / (R)2) * w) * (R)0.5;
+							gmag *= fov_factor<R>(arel, 1, fovh, fovg, fovn);
+						}
+						gmag = valid ? gmag : (R)0;
+						fsx = fmaf(gmag, ex, fsx);
+						fsy = fmaf(gmag, ey, fsy);
+					};
+					if (P.fov_method == 0) {
+#pragma unroll TPC_UNROLL
+						for (int j = 0; j < ns; ++j) static_body(std::true_type{}, j);
+					} else {
+#pragma unroll 1
+						for (int j = 0; j < ns; ++j) static_body(std::false_type{}, j);
+					}
+				}
+				// -- dynamic objects (social_force_model.cpp:338-436) + fuzzy human-action force --
+				{
+					const int nd = (i == 0) ? S.n_dynamic : S.n_dynamic_later;
+					const R nine = (R)9 * Cst<R>::deg();
+					const R speed_r = speed_d;
+#pragma unroll 1
+					for (int k = 0; k < nd; ++k) {
+						const DevDynamic& o = dynamics[k];
+						R dx = (R)(fma(tnow, o.vx, o.d0x) - rxd), dy = (R)(fma(tnow, o.vy, o.d0y) - ryd);
+						R dist = sqrt_nr(dx * dx + dy * dy);
+						dmin = fminf(dmin, dist);
+						if (!forces_on) continue;
+						// World::computeObjectRelativeLocation, world.cpp:192-229 (un-normalised difference)
+						R angle_d = atan2_r(dy, dx);
+						R rel = angle_d - (R)wrapd(o.psi0 + dpsi);
+						R arel = fabsf(rel);
+						R side = (arel <= nine || arel >= Cst<R>::pi() - nine) ? (R)0 : ((rel <= (R)0) ? (R)-1 : (R)1);
+						R rel_loc = wrapf(rel);
+						if (dist <= (R)7.5) {
+							R vrx = (R)o.vx - ux, vry = (R)o.vy - uy;
+							R vrel = sqrtf(vrx * vrx + vry * vry);
+							if (vrel >= (R)1e-6) {
+								R fov = fov_factor<R>(rel_loc, P.fov_method, fovh, fovg, fovn);
+								R thab = wrapf(th_r - angle_d);
+								R en = An * expf(((-Bn * thab * thab) / vrel) - Cn * dist) * fov;
+								R ep = Ap * expf(((-Bp * fabsf(thab)) / vrel) - Cp * dist) * fov * side;
+								// n = (c, s); p = side * (s, -c)  (LEFT: n x z, RIGHT: n x -z)
+								fdx_r += c_r * en + s_r * ep;
+								fdy_r += s_r * en - c_r * ep;
+							}
+						}
+						if (P.fis_on && dist <= (R)P.fis_range_d) {
+							// social_conductor.cpp:37-105, :162-179
+							R strength = (expf(speed_r + (R)o.speed) - (R)1) * expf(-dist);
+							R val, mu;
+							fis_process<R>(heading_r, (R)o.dir_beta, rel_loc, angle_d, val, mu);
+							if (mu > (R)0) {
+								R ff = (R)1;
+								if (P.fis_fov_method == 0 || P.fis_fov_method == 1)
+									ff = fov_factor<R>(rel_loc, P.fis_fov_method, (R)P.fis_fov_half_d, (R)P.fis_gauss_scale_d,
+									                   (R)P.fis_neg_inv_2var_d);
+								R mag = As * mu * strength * ff;
+								R sv, cv;
+								sincosf(val, &sv, &cv);
+								fhx = fmaf(mag, cv, fhx);
+								fhy = fmaf(mag, sv, fhy);
+							}
+						}
+					}
+				}
+				// TTC: first world index whose running minimum distance is within the collision distance
+				// (ttc_cost_function.cpp:72-82)
+				ttc_min = fminf(ttc_min, dmin);
+				if (ttc_min <= P.ttc_collision_distance) ttc_first = min(ttc_first, i);
+
+				const SC cs = (SC)cd, ss = (SC)sd;
+				SC Fsx = fsx, Fsy = fsy, fdx = fdx_r, fdy = fdy_r;
+				SC Fhx = 0, Fhy = 0;
+				if (P.fis_on) {
+					// rotate to the global frame, x force_factor (social_conductor.cpp:96-104)
+					Fhx = (fhx * cs - fhy * ss) * (SC)P.fis_force_factor_d;
+					Fhy = (fhx * ss + fhy * cs) * (SC)P.fis_force_factor_d;
+				}
+				// factorInForceCoefficients + applyNonlinearOperations (social_force_model.cpp:745-881)
+				fix *= (SC)P.k_int;
+				fiy *= (SC)P.k_int;
+				Fsx *= (SC)P.k_stat;
+				Fsy *= (SC)P.k_stat;
+				fdx *= (SC)P.k_dyn;
+				fdy *= (SC)P.k_dyn;
+				if (P.filter_forces) {
+					SC cx = fix + fdx + Fsx, cy = fiy + fdy + Fsy;
+					SC mag = sqrt_s(cx * cx + cy * cy);
+					if (mag >= (SC)P.max_force) {
+						SC k = (SC)P.max_force / mag;
+						fix *= k; fiy *= k; fdx *= k; fdy *= k; Fsx *= k; Fsy *= k;
+					} else if (mag <= (SC)P.min_force) {
+						SC ext = fabsf(mag - (SC)P.min_force);
+						SC inv = (mag <= (SC)1e-6) ? (SC)1 : (SC)1 / mag;
+						fdx += ext * cx * inv;
+						fdy += ext * cy * inv;
+					}
+				}
+				// -- computeTwist (transformations.cpp:61-126) --
+				const SC Fx = fix + fdx + Fsx + Fhx, Fy = fiy + fdy + Fsy + Fhy;
+				const bool has_force = !((Fx * Fx + Fy * Fy) <= 1e-16f);   // |F| <= 1e-8 without the sqrt
+				if (has_force && !(P.mass <= 1e-6)) {
+					SC ax = Fx / (SC)P.mass, ay = Fy / (SC)P.mass;
+					SC vv = cs * ax + ss * ay;
+					const SC vcross = -ss * ax + cs * ay;
+					// angle of the force relative to the yaw: polynomial atan2 of (F . e_yaw, F x e_yaw), no wrap needed
+					SC ang = atan2_r(vcross, vv);
+					SC vw = vcross + (SC)P.rot_comp * ang;
+					tw = saturate_velocity<SC>({vv, 0, vw}, (SC)P.max_vel_x, (SC)0, (SC)P.max_vel_x, (SC)P.max_vel_theta, (SC)P.back_max);
+				}
+				// -- adjustTwistWithAccAndGoalLimits (transformations.cpp:257-317 -> :199-255) --
+				{
+					TwistS vl = {ux * cs + uy * ss, 0, uw};  // computeVelocityLocal, non-holonomic
+					SC smax = sqrt_s((SC)2 * (SC)P.acc_decel * goal_dist);
+					SC ca = 1, sa = 0;
+					if (fabsf(vl.x) >= (SC)1e-4 || fabsf(vl.y) >= (SC)1e-4) {
+						// cos / sin of atan2(cmd.y, cmd.x) without the trigonometry (atan2(0, 0) = 0 -> (1, 0))
+						SC tl = sqrt_s(tw.x * tw.x + tw.y * tw.y);
+						if (tl > (SC)0) {
+							ca = tw.x / tl;
+							sa = tw.y / tl;
+						} else if (signbit(tw.x)) {
+							ca = -1;   // atan2(+-0, -0) = +-pi
+						}
+					}
+					const SC adt_x = (SC)P.acc_x * (SC)P.dt_d, adt_y = (SC)P.acc_y * (SC)P.dt_d, adt_w = (SC)P.acc_th * (SC)P.dt_d;
+					SC max_x = fmaxf(fminf((SC)P.max_vel_x, ca * smax), (SC)P.min_vel_x);
+					SC max_y = fmaxf(fminf((SC)P.max_vel_y, sa * smax), (SC)P.min_vel_y);
+					SC lo_x = fmaxf((SC)P.min_vel_x, vl.x - adt_x), hi_x = fminf(max_x, vl.x + adt_x);
+					SC lo_y = fmaxf((SC)P.min_vel_y, vl.y - adt_y), hi_y = fminf(max_y, vl.y + adt_y);
+					SC lo_w = fmaxf(-(SC)P.max_vel_theta, vl.w - adt_w), hi_w = fminf((SC)P.max_vel_theta, vl.w + adt_w);
+					if (!P.maintain_rate) {
+						tw.x = fminf(fmaxf(lo_x, tw.x), hi_x);
+						tw.y = fminf(fmaxf(lo_y, tw.y), hi_y);
+						tw.w = fminf(fmaxf(lo_w, tw.w), hi_w);
+					} else {
+						tw = adjust_proportional<SC>(vl, tw, lo_x, lo_y, lo_w, hi_x, hi_y, hi_w);
+					}
+				}
+				// -- areVelocityLimitsFulfilled (social_trajectory_generator.cpp:556-582) --
+				{
+					SC sl = sqrt_s(tw.x * tw.x + tw.y * tw.y);
+					bool trans_wrong = (P.min_vel_trans >= 0.0) && ((sl + (SC)1e-4) < (SC)P.min_vel_trans);
+					bool theta_wrong = (P.min_vel_theta >= 0.0) && ((fabsf(tw.w) + (SC)1e-4) < (SC)P.min_vel_theta);
+					if ((trans_wrong && theta_wrong) || ((P.max_vel_trans >= 0.0) && ((sl - (SC)1e-4) > (SC)P.max_vel_trans))) {
+						rejected = true;
+						alive = false;
+					}
+				}
+				if (alive) {
+					if (i == 0) {
+						seed_x = tw.x;
+						seed_w = tw.w;
+					}
+					tgx_d = tw.x * cs - tw.y * ss;   // computeVelocityGlobal
+					tgy_d = tw.x * ss + tw.y * cs;
+				}
+			}
+
+			// =============================== critics on pose i ==========================================
+			// ObstacleSeparationCostFunction (obstacle_separation_cost_function.cpp:85-114): the dilated-map test is per
+			// thread, the poses that must be rasterised are walked one after the other by the whole warp
+			{
+				bool need = alive && ob_on && !ob_neg;
+				if (need && dil != nullptr) {
+					int mx, my;
+					if (world_to_map(G, x, y, mx, my)) {
+						const int dmax = (int)__ldg(&dil[my * G.sx + mx]);
+						// dmax < 254: no lethal / unknown cell in reach (see plan_kernel)
+						const bool skip = P.occdist_sum ? (dmax == 0) : (dmax <= ob_best && dmax < 254);
+						need = !skip;
+					}
+				}
+				unsigned m = __ballot_sync(0xffffffffu, need);
+				while (m) {
+					const int src = __ffs(m) - 1;
+					m &= m - 1;
+					const double bx = __shfl_sync(0xffffffffu, x, src), by = __shfl_sync(0xffffffffu, y, src);
+					const double bc = __shfl_sync(0xffffffffu, cd, src), bs = __shfl_sync(0xffffffffu, sd, src);
+					bool neg = false;
+					int best = 0;
+					footprint_pose(P, G, cm, bx, by, bc, bs, lane, neg, best);
+					const bool any_neg = __any_sync(0xffffffffu, neg);  // the first negative pose aborts the critic (-6)
+					best = __reduce_max_sync(0xffffffffu, best);
+					if (lane == src) {
+						ob_neg = any_neg;
+						if (P.occdist_sum) ob_sum += (float)best;
+						else ob_best = max(ob_best, best);
+					}
+				}
+			}
+			if (alive) {
+				const float rx = (float)(x - S.x0), ry = (float)(y - S.y0);
+				// a negative obstacle cost aborts the scoring of this trajectory (SimpleScoredSamplingPlanner): the remaining
+				// critics are never evaluated by the reference, only the rollout continues (the generator may still reject it)
+				const bool dead = ob_neg && ob_on;
+				// MapGridCostFunction x4 (map_grid_cost_function.cpp:142-196, :81-140)
+				if (!dead) {
+#pragma unroll
+					for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+						if ((mg_codes >> (8 * g)) & 0xff) continue;
+						double px = x, py = y;
+						if (P.mg_xshift[g] != 0.0) {
+							px += P.mg_xshift[g] * cd;
+							py += P.mg_xshift[g] * sd;
+						}
+						if (P.mg_yshift[g] != 0.0) {
+							px += P.mg_yshift[g] * (-sd);
+							py += P.mg_yshift[g] * cd;
+						}
+						int mx, my;
+						if (!world_to_map(G, px, py, mx, my)) {
+							mg_codes |= 4 << (8 * g);
+						} else {
+							float v = __ldg(&mapgrids[(size_t)g * grid_cells + (size_t)my * P.size_x + mx]);
+							if (v != unreachable_costs || P.mg_kernel[g] <= 0) {
+								if (v != obstacle_costs) mg_hv[g] = fmaxf(mg_hv[g], v);
+							} else {
+								// the neighbourhood list starts with the unreachable cell itself (see plan_kernel)
+								v = (float)S.hv_prev[g];
+							}
+							if (P.mg_stop_on_failure[g]) {
+								if (v == obstacle_costs) mg_codes |= 3 << (8 * g);
+								else if (v == unreachable_costs) mg_codes |= 2 << (8 * g);
+							}
+							mg_last[g] = v;
+						}
+					}
+				}
+				// velocity-based critics use velocity i of the wrapped Trajectory (exists for i == 0 or i <= T - 2)
+				if (i < n_vel) {
+					last_tgx = tgx_d;
+					last_tgy = tgy_d;
+					// UnsaturatedTranslationCostFunction (:31-87)
+					if (i == 0 || P.unsat_whole) {
+						un_x += fabsf(tw.x - P.unsat_max_x);
+						un_y += fabsf(tw.y - P.unsat_max_y);
+						un_xy += fabsf(hypotf(tw.x, tw.y) - P.unsat_max_trans);
+						un_n++;
+					}
+					// HeadingChangeSmoothness (:15-43), VelocitySmoothness (:18-50)
+					if (i == 0) {
+						hcs = fabsf(tw.w - S.vlw);
+						vsm_x = fabsf(tw.x - S.vlx);
+						vsm_y = fabsf(tw.y - S.vly);
+					} else {
+						hcs += fabsf(tw.w - prev_tw.w) / dt;
+						vsm_x += fabsf(tw.x - prev_tw.x);
+						vsm_y += fabsf(tw.y - prev_tw.y);
+					}
+					prev_tw = tw;
+					// people critics: heading disturbance, personal space, passing speed
+					const bool do_hd = (i == 0 || P.hd_whole) && P.scale[HMP_COST_HEADING_DIST] != 0.0;
+					const bool do_psi = (i == 0 || P.psi_whole) && P.scale[HMP_COST_PERSONAL_SPACE] != 0.0;
+					const bool do_ps = (i == 0 || P.ps_whole) && P.scale[HMP_COST_PASSING_SPEED] != 0.0;
+					if (!dead && (do_hd || do_psi || do_ps)) {
+						const float tp = (float)i * P.people_dt;
+						const float rspeed = hypotf(tgx_d, tgy_d);
+						const float motion_dir = atan2_r(tgy_d, tgx_d);
+						const float sp_norm = fminf(fmaxf(rspeed * P.ps_inv_max_speed, 0.0f), 1.0f);
+#pragma unroll 1
+						for (int p = 0; p < S.n_people; ++p) {
+							const float4 a0 = reinterpret_cast<const float4*>(people)[4 * p];
+							const float4 a1 = reinterpret_cast<const float4*>(people)[4 * p + 1];
+							const float4 a2 = reinterpret_cast<const float4*>(people)[4 * p + 2];
+							const float4 a3 = reinterpret_cast<const float4*>(people)[4 * p + 3];
+							float pxp = fmaf(tp, a1.x, a0.x), pyp = fmaf(tp, a1.y, a0.y);
+							float dx = rx - pxp, dy = ry - pyp;
+							float dist = sqrt_nr(dx * dx + dy * dy);
+							float yawp = a0.z, cp = a1.z, sp = a1.w;
+							if (a0.w != 0.0f) {   // warp-uniform (a property of the person)
+								yawp = wrapf(fmaf(tp, a0.w, a0.z));
+								sincosf(yawp, &sp, &cp);
+							}
+							if (do_psi) {
+								// personal_space_intrusion_cost_function.cpp:55-78 (asymmetric Gaussian, peak 1)
+								float along = dx * cp + dy * sp;
+								float vh = (along >= 0.0f) ? a3.x : a3.y;
+								float vs = a3.z;
+								float ga = vh * cp * cp + vs * sp * sp + a2.x;
+								float gb = (vh - vs) * cp * sp;
+								float gc = vh * sp * sp + vs * cp * cp + a2.w;
+								float b1 = gb + a2.y, b2 = gb + a2.z;
+								float det = ga * gc - b1 * b2;
+								float q = (gc * dx * dx - (b1 + b2) * dx * dy + ga * dy * dy) / det;
+								psi_max = fmaxf(psi_max, __expf(-0.5f * q));
+							}
+							if (do_hd) {
+								// heading_disturbance_cost_function.cpp:69-86
+								float v = 0.0f;
+								if (!(rspeed < 1e-9f) && !(dist < 1e-9f)) {
+									float dist_angle = atan2_r(dy, dx);
+									float rel_loc = wrapf(dist_angle - yawp);
+									float gamma_cc = wrapf(dist_angle + PI_F);
+									float half = atan2_r(a3.w, dist);
+									float dd = wrapf(motion_dir - gamma_cc);
+									float g_dir = __expf(-(dd * dd) / (2.0f * half * half));
+									float g_fov = __expf(rel_loc * rel_loc * P.hd_neg_inv_2var_fov);
+									v = g_dir * g_fov * (rspeed * P.hd_inv_max_speed) * (P.hd_dmin / fmaxf(dist, P.hd_dmin));
+								}
+								hd_max = fmaxf(hd_max, v);
+							}
+							if (do_ps) {
+								// passing_speed_cost_function.cpp:57-71
+								float clearance = fmaxf(dist - P.ps_min_dist, 0.0f);
+								ps_max = fmaxf(ps_max, sp_norm * __expf(-clearance));
+							}
+						}
+					}
+				}
+				// FformationSpaceIntrusion (:39-78): every pose
+				if (!dead && (i == 0 || P.fsi_whole) && P.scale[HMP_COST_FFORMATION] != 0.0) {
+#pragma unroll 1
+					for (int gidx = 0; gidx < S.n_groups; ++gidx) {
+						const float4 g0 = reinterpret_cast<const float4*>(groups)[2 * gidx];
+						const float ic = groups[gidx].ic;
+						float dx = rx - g0.x, dy = ry - g0.y;
+						float q = g0.z * dx * dx + 2.0f * g0.w * dx * dy + ic * dy * dy;
+						fsi_max = fmaxf(fsi_max, __expf(-0.5f * q));
+					}
+				}
+				// -- World::predict (world.cpp:86-114): integrate the centroid in FP64 --
+				x += tgx_d * P.dt_d;
+				y += tgy_d * P.dt_d;
+				th = wrapd(th + tw.w * P.dt_d);
+				ux = tgx_d;
+				uy = tgy_d;
+				uw = tw.w;
+			}
+		}
+
+		// ---- TTC look-ahead (ttc_cost_function.cpp:96-134): constant-velocity continuation -------------
+		if (active && !rejected && P.scale[HMP_COST_TTC] != 0.0) {
+			const int n_main = 1 + n_vel;  // worlds built by World::predict(Trajectory)
+			const int n_post = (n_main - T) + max(P.n_ttc_extra - 1, 0);
+			// pose of world T - 1 is (x, y) minus the last integration step
+			double bx = x - ux * P.dt_d, by = y - uy * P.dt_d;
+			for (int j = 1; j <= n_post; ++j) {
+				double rxd = bx + (SC)last_tgx * P.dt_d * j - S.x0;
+				double ryd = by + (SC)last_tgy * P.dt_d * j - S.y0;
+				double tnow = (double)(T - 1 + j) * P.dt_d;
+				float dmin = CUDART_INF_F;
+				for (int jj = 0; jj < S.n_static; ++jj) {
+					const double2 o = reinterpret_cast<const double2*>(statics)[jj];
+					float dx = (float)(o.x - rxd), dy = (float)(o.y - ryd);
+					dmin = fminf(dmin, sqrtf(dx * dx + dy * dy));
+				}
+				for (int k = 0; k < S.n_dynamic_later; ++k) {
+					const DevDynamic& o = dynamics[k];
+					double dx = fma(tnow, o.vx, o.d0x) - rxd, dy = fma(tnow, o.vy, o.d0y) - ryd;
+					dmin = fminf(dmin, (float)sqrt(dx * dx + dy * dy));
+				}
+				ttc_min = fminf(ttc_min, dmin);
+				// world T - 1 + j is checked with timestamp (T + j) * dt when it comes from the look-ahead loop
+				int stamp = (j <= n_main - T) ? (T - 1 + j) : (T + j);
+				if (ttc_min <= P.ttc_collision_distance) ttc_first = min(ttc_first, stamp);
+			}
+		}
+
+		// ---- the weighted total (SimpleScoredSamplingPlanner) -------------------------------------------
+		double total = -1.0;
+		int n_eval_grids = 0;  // MapGrid critics actually evaluated (for highest_valid_cost_)
+		if (active && !rejected) {
+			n_generated++;
+			double raw[HMP_NUM_COSTS];
+			raw[HMP_COST_OBSTACLE] = (P.n_footprint == 0) ? -9.0 : (ob_neg ? -6.0 : (P.occdist_sum ? (double)ob_sum : (double)ob_best));
+#pragma unroll
+			for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+				const int code = (mg_codes >> (8 * g)) & 0xff;
+				raw[HMP_COST_PATH + g] = code ? -(double)code : (double)mg_last[g];
+			}
+			raw[HMP_COST_UNSATURATED] = (un_n > 0) ? (double)(fmaxf(fmaxf(un_x, un_y), un_xy) / (float)un_n) : 0.0;
+			// PreferForwardCostFunction
+			raw[HMP_COST_BACKWARD] = (seed_x < 0.0 || (seed_x < 0.1 && fabsf(seed_w) < 0.2)) ? (double)P.backward_penalty
+			                                                                                 : (double)(fabsf(seed_w) * 10);
+			{
+				double c = 0.0;
+				if (ttc_first != 0x7fffffff) {
+					double ttc = (double)ttc_first * P.dt_d;
+					if (ttc <= 0.0) ttc = 1e-4;
+					c = ((double)T * P.dt_d + P.ttc_rollout_time_d) / ttc;
+				}
+				raw[HMP_COST_TTC] = c;
+			}
+			raw[HMP_COST_HEADING_CHANGE] = (double)(hcs / (float)(n_vel + 1));
+			raw[HMP_COST_VEL_SMOOTHNESS] = (double)((vsm_x + vsm_y) / (float)(n_vel + 1));
+			raw[HMP_COST_HEADING_DIST] = (S.n_people > 0) ? (double)hd_max : 0.0;
+			raw[HMP_COST_PERSONAL_SPACE] = (S.n_people > 0) ? (double)psi_max : 0.0;
+			raw[HMP_COST_FFORMATION] = (S.n_groups > 0) ? (double)fsi_max : 0.0;
+			raw[HMP_COST_PASSING_SPEED] = (S.n_people > 0) ? (double)ps_max : 0.0;
+
+			total = 0.0;
+			bool aborted = false;
+#pragma unroll
+			for (int k = 0; k < HMP_NUM_COSTS; ++k) {
+				double sc = P.scale[k];
+				if (sc == 0.0 || aborted) continue;
+				if (k >= HMP_COST_PATH && k <= HMP_COST_GOAL_FRONT) n_eval_grids |= 1 << (k - HMP_COST_PATH);
+				double cst = raw[k];
+				if (cst < 0.0) {
+					total = cst;
+					aborted = true;
+					continue;
+				}
+				if (cst != 0.0) cst *= sc;
+				total += cst;
+			}
+			if (total >= 0.0) {
+				n_valid++;
+				if (tbest < 0.0 || total < tbest || (total == tbest && cand < tbest_idx)) {
+					tbest = total;
+					tbest_idx = cand;
+				}
+			}
+		}
+		// highest_valid_cost_ of the four MapGrid critics: max over the warp's candidates, one atomic per warp and grid
+#pragma unroll
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+			unsigned int hvb = (((n_eval_grids >> g) & 1) && mg_hv[g] > 0.0f) ? __float_as_uint(mg_hv[g]) : 0u;
+			hvb = __reduce_max_sync(0xffffffffu, hvb);   // positive floats order like their bit patterns
+			if (lane == 0 && hvb) atomicMax(&s_hv[g], hvb);
+		}
+		if (active && A.totals) A.totals[(size_t)scene * P.n_candidates + cand] = total;
+	}
+
+	// ---- selection: thread -> warp -> block argmin -> last block merges (strict '<', lowest index wins ties) ----
+	{
+		unsigned long long bk = (tbest_idx >= 0) ? cost_key(tbest) : ~0ull;
+		int bi = tbest_idx;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+			int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (oi >= 0 && (bi < 0 || ok < bk || (ok == bk && oi < bi))) {
+				bk = ok;
+				bi = oi;
+			}
+		}
+		n_generated = __reduce_add_sync(0xffffffffu, n_generated);
+		n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+		if (lane == 0) {
+			s_wbest[warp] = (bi >= 0) ? __longlong_as_double((long long)bk) : -1.0;
+			s_widx[warp] = bi;
+			atomicAdd(&s_cnt[0], n_generated);
+			atomicAdd(&s_cnt[1], n_valid);
+		}
+	}
+	__syncthreads();
+	if (tid == 0) {
+		double b = -1.0;
+		int bi = -1;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+			double v = s_wbest[w];
+			int vi = s_widx[w];
+			if (vi >= 0 && v >= 0.0 && (b < 0.0 || v < b || (v == b && vi < bi))) {
+				b = v;
+				bi = vi;
+			}
+		}
+		unsigned long long* bb = A.block_best + ((size_t)scene * gridDim.x + blockIdx.x) * 2;
+		bb[0] = (bi >= 0) ? cost_key(b) : ~0ull;
+		bb[1] = (unsigned long long)(long long)bi;
+		atomicAdd(&counters[2], s_cnt[0]);
+		atomicAdd(&counters[3], s_cnt[1]);
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g)
+			if (s_hv[g]) atomicMax(&A.hv_out[(size_t)scene * HMP_NUM_MAPGRIDS + g], s_hv[g]);
+		__threadfence();
+		unsigned int done = atomicAdd(&counters[1], 1u);
+		s_last = (done == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (s_last && warp == 0) {
+		__threadfence();
+		unsigned long long bk = ~0ull;
+		long long bi = -1;
+		const volatile unsigned long long* bb = A.block_best + (size_t)scene * gridDim.x * 2;
+		for (int b = lane; b < (int)gridDim.x; b += 32) {
+			unsigned long long k = bb[2 * b];
+			long long idx = (long long)bb[2 * b + 1];
+			if (idx >= 0 && (k < bk || (k == bk && idx < bi))) {
+				bk = k;
+				bi = idx;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+			long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (oi >= 0 && (bi < 0 || ok < bk || (ok == bk && oi < bi))) {
+				bk = ok;
+				bi = oi;
+			}
+		}
+		if (lane == 0) {
+			if (A.best_init) {
+				// best of an earlier sweep over other candidates of the same pool (the equisampled generator's)
+				const double it = A.best_init[(size_t)scene * 2];
+				const long long ii = (long long)A.best_init[(size_t)scene * 2 + 1];
+				if (ii >= 0 && (bi < 0 || cost_key(it) < bk || (cost_key(it) == bk && ii < bi))) {
+					bk = cost_key(it);
+					bi = ii;
+				}
+			}
+			A.best_out[(size_t)scene * 2 + 0] = (bi >= 0) ? __longlong_as_double((long long)bk) : -7.0;
+			A.best_out[(size_t)scene * 2 + 1] = (double)bi;
+		}
+	}
+}

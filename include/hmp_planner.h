@@ -325,6 +325,14 @@ int hmp_set_precision(HmpContext* ctx, int32_t fp64);
 int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders);
 /* Leaders re-scored in FP64 by the last plan of scene 0 (0 in modes 0 / 1), -1 if there is no plan. */
 int hmp_last_num_leaders(HmpContext* ctx);
+/* Work layout of the FP32 sweep (modes 0 and 2): 0 (default) = automatic, 1 = one warp per candidate (lanes stride over the
+ * objects; shortest latency for a few thousand candidates), 2 = one thread per candidate (a warp rolls out 32 candidates,
+ * the per-step scalar section is issued once per 32; highest throughput from ~16k candidates per launch). Both layouts
+ * evaluate the same FP32 arithmetic; only the summation order of the interaction forces differs. The environment variable
+ * HMP_SWEEP_LAYOUT presets it at hmp_create. No reference counterpart. */
+int hmp_set_sweep_layout(HmpContext* ctx, int32_t layout);
+/* Layout the last plan's main sweep ran with: 0 = warp per candidate, else the block size of the thread-per-candidate kernel. */
+int hmp_last_sweep_mode(HmpContext* ctx);
 
 /* Replaces the costmap_2d::Costmap2D* every critic holds (row-major, index = my * size_x + mx). */
 int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y,

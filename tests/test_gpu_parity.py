@@ -35,6 +35,14 @@ def _setup(planner, name, seed, fis=True, mutate=None, precise=False):
     return cfg, sc, params, smp
 
 
+@pytest.fixture(params=[1, 2], ids=["warp", "thread"])
+def layout(request, planner):
+    """Work layout of the FP32 sweep (hmp_set_sweep_layout): one warp per candidate / one thread per candidate."""
+    planner.set_sweep_layout(request.param)
+    yield request.param
+    planner.set_sweep_layout(0)
+
+
 def _rel_err(g, o):
     return np.abs(g - o) / np.maximum(np.abs(o), 1e-6)
 
@@ -307,9 +315,10 @@ def _check_totals(cycle, o):
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
-def test_selection_cfg0(planner, seed):
+def test_selection_cfg0(planner, seed, layout):
     cfg, sc, params, smp = _setup(planner, "cfg0", seed)
     res, poses = planner.plan(sc.world, smp)
+    assert (planner.last_sweep_mode() != 0) == (layout == 2)
     ref = ob.plan(params, sc, smp, early_exit=True)       # the reference's own early-exit semantics
     r = ref["result"]
     assert res.n_candidates == r.n_candidates == 72
@@ -349,9 +358,10 @@ def test_selection_cfg1_full_grid(planner):
 # ---------------------------------------------------------------------------------------------------------------
 # size-independent properties at the full BASELINE size (64k candidates x 50 people x 500 obstacle points)
 # ---------------------------------------------------------------------------------------------------------------
-def test_full_size_properties_cfg2(planner):
+def test_full_size_properties_cfg2(planner, layout):
     cfg, sc, params, smp = _setup(planner, "cfg2", 0)
     res, poses = planner.plan(sc.world, smp)
+    assert (planner.last_sweep_mode() != 0) == (layout == 2)
     Cn = res.n_candidates
     assert Cn == 65536 and planner.num_steps() == 50
     t1 = planner.explored_totals(Cn)
@@ -360,13 +370,14 @@ def test_full_size_properties_cfg2(planner):
     assert res.n_valid == len(valid) and res.n_generated == int((t1 != -1.0).sum())
     best = valid[np.argmin(t1[valid])]
     assert res.best_index == best and res.best_total == t1[best]
-    # the winner's detail pass reproduces the selection pass bit for bit
+    # the winner's detail pass (always one warp per candidate) reproduces the selection pass: bit for bit when the sweep
+    # has the same layout, to FP32 summation-order noise when the sweep ran one thread per candidate
     ex = planner.explain([int(best)])
     assert ex["n_poses"][0] == 50 and np.array_equal(ex["poses"][0], poses)
     assert np.array_equal(np.array(res.costs), ex["costs"][0], equal_nan=True)
     scale = np.array(params.costs.scale)
     c = ex["costs"][0]
-    assert abs(np.nansum(np.where(c != 0, c * scale, c)) - res.best_total) <= 1e-9 * abs(res.best_total)
+    assert abs(np.nansum(np.where(c != 0, c * scale, c)) - res.best_total) <= (1e-9 if layout == 1 else 1e-5) * abs(res.best_total)
     # determinism: a second run over resident inputs gives identical totals
     r2 = planner.replan_resident()[0]
     assert r2.best_index == res.best_index and r2.best_total == res.best_total
@@ -382,6 +393,40 @@ def test_full_size_properties_cfg2(planner):
     tx = planner.explored_totals(rx.n_candidates)
     assert rx.n_candidates == 1 + len(pick)
     assert np.array_equal(tx[1:], t1[pick])
+
+
+@pytest.mark.parametrize("name,seed", [("cfg0", 0), ("cfg1", 0), ("cfg1", 3), ("cfg2", 0)])
+def test_sweep_layouts_agree(planner, name, seed):
+    """The two work layouts of the FP32 sweep evaluate the same arithmetic; only the summation order of the forces differs.
+    Codes of invalid candidates, counters and highest_valid_cost_ agree, totals agree to FP32 noise for the bulk (chaotic
+    candidates amplify the noise), and with the FP64 refinement (mode 2) the decision is identical."""
+    out = {}
+    for lay in (1, 2):
+        cfg, sc, params, smp = _setup(planner, name, seed)
+        planner.set_sweep_layout(lay)
+        try:
+            res, _ = planner.plan(sc.world, smp, want_poses=False)
+            assert (planner.last_sweep_mode() != 0) == (lay == 2)
+            tot = planner.explored_totals(res.n_candidates)
+            planner.set_precision(2)
+            ref, _ = planner.plan(sc.world, smp, want_poses=False)
+        finally:
+            planner.set_sweep_layout(0)
+            planner.set_precision(False)
+        out[lay] = (res, tot, ref)
+    (ra, ta, fa), (rb, tb, fb) = out[1], out[2]
+    assert ra.n_candidates == rb.n_candidates and ra.n_generated == rb.n_generated
+    same_sign = (ta < 0) == (tb < 0)
+    assert same_sign.mean() >= 0.999
+    neg = (ta < 0) & (tb < 0)
+    assert np.array_equal(ta[neg], tb[neg])
+    assert abs(ra.n_valid - rb.n_valid) <= max(1, 0.001 * ra.n_candidates)
+    v = (ta >= 0) & (tb >= 0)
+    rel = _rel_err(ta[v], tb[v])
+    assert np.median(rel) < 1e-6 and (rel > 1e-3).mean() <= 0.05
+    assert np.allclose(np.array(ra.highest_valid_cost), np.array(rb.highest_valid_cost))
+    assert abs(ra.best_total - rb.best_total) <= 1e-4 * abs(ra.best_total)
+    assert fa.best_index == fb.best_index and fa.best_total == fb.best_total
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -460,10 +505,14 @@ VARIANTS = [_m_fis_off, _m_filter, _m_linear_fov, _m_maintain, _m_ttc_rollout, _
 
 @pytest.mark.parametrize("precise", [True, False], ids=["fp64", "fp32"])
 @pytest.mark.parametrize("mutate", VARIANTS, ids=lambda f: f.__name__[3:])
-def test_parameter_variants(planner, mutate, precise):
+def test_parameter_variants(planner, mutate, precise, layout):
     """Every configuration branch of the path. FP64 mode checks the LOGIC of each branch strictly (poses to 1e-8);
-    FP32 mode checks that the fast path follows it within the north_star tolerances for the bulk of the candidates."""
+    FP32 mode checks that the fast path follows it within the north_star tolerances for the bulk of the candidates
+    (explored totals from the sweep in both layouts, poses / critics from the detail pass)."""
+    if precise and layout == 2:
+        pytest.skip("the FP64 sweep has one layout")
     cy = _cycle(planner, "cfg0", 1, 72, mutate=mutate, precise=precise)
+    assert (planner.last_sweep_mode() != 0) == (layout == 2 and not precise)
     planner.set_precision(False)
     g, o = cy["totals"][cy["idx"]], cy["orc"]["totals"]
     assert ((g < 0) == (o < 0)).mean() >= (1.0 if precise else 0.97)
@@ -499,7 +548,7 @@ def test_parameter_variants(planner, mutate, precise):
 # ---------------------------------------------------------------------------------------------------------------
 # batched scenes (BASELINE config 4): one launch over n scenes == n single-scene cycles
 # ---------------------------------------------------------------------------------------------------------------
-def test_batched_scenes_equal_single_cycles(planner):
+def test_batched_scenes_equal_single_cycles(planner, layout):
     planner.set_precision(False)
     cfg = scenes.CONFIGS["cfg3"]
     params = scenes.make_params(cfg)
@@ -559,7 +608,7 @@ def test_cycle_with_device_wavefront_equals_uploaded_grids(planner):
     assert np.array_equal(planner.explored_totals(r2.n_candidates), t1) and np.array_equal(p1, p2)
 
 
-def test_batch_64_scenes(planner):
+def test_batch_64_scenes(planner, layout):
     """A slice of BASELINE config 4 (batched independent scenes, 4k candidates each): every scene's argmin equals the
     argmin of its explored totals, and sampled scenes equal their single-scene cycle."""
     planner.set_precision(False)
@@ -706,7 +755,7 @@ def test_refinement_window_and_cap(planner):
     assert abs(res32.best_total - res.best_total) <= 1e-4 * abs(res.best_total)
 
 
-def test_refined_batch_equals_single_cycles(planner):
+def test_refined_batch_equals_single_cycles(planner, layout):
     """hmp_plan_batch in mode 2: per-scene leaders lists, same winners as scene-by-scene refined plans."""
     cfg = scenes.CONFIGS["cfg3"]
     params = scenes.make_params(cfg)
@@ -741,7 +790,7 @@ def _pentagon(r=0.3):
 @pytest.mark.parametrize("name,seed,variant", [("cfg0", 0, "default"), ("cfg0", 1, "sum"), ("cfg1", 1, "default"),
                                                 ("cfg1", 2, "cross"), ("cfg2", 1, "default"), ("cfg0", 3, "pentagon"),
                                                 ("cfg0", 5, "nosep"), ("cfg1", 3, "moved")])
-def test_obstacle_pruning_is_exact(planner, name, seed, variant):
+def test_obstacle_pruning_is_exact(planner, name, seed, variant, layout):
     import os
     from humap_local_planner_b200 import Planner
     cfg = scenes.CONFIGS[name]
@@ -764,6 +813,7 @@ def test_obstacle_pruning_is_exact(planner, name, seed, variant):
         finally:
             os.environ.pop("HMP_NO_PRUNE", None)
         pl.set_precision(0)
+        pl.set_sweep_layout(layout)
         pl.set_params(params)
         pl.set_scene(sc)
         if variant == "pentagon":
