@@ -31,6 +31,7 @@ extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_occupancy_tpc(size_t smem, int threads, int* blocks_per_sm);
 extern "C" int hmp_dev_tpc_max_threads();
+extern "C" size_t hmp_dev_tpc_extra_smem(uint32_t scene_stride);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_env_filter(const HmpShape* shapes, int n_shapes, const double* verts, const HmpPerson* people, int n_people,
                                                  double person_radius, double containment_rate, double rx, double ry, int32_t* keep,
@@ -601,7 +602,7 @@ struct PlanLaunch {
 };
 
 int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* blocks_x_out, size_t* smem_out,
-                int* costmap_in_smem_out, int* sweep_mode_out = nullptr) {
+                int* costmap_in_smem_out, int* sweep_mode_out = nullptr, size_t* smem_sweep_out = nullptr) {
 	const int C = D.n_social;
 	size_t cm_bytes = (size_t)ctx->costmap_stride;
 	int in_smem = 1;
@@ -627,8 +628,16 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes < ctx->sm_count) tpc_threads /= 2;
 		}
 	}
+	size_t smem_sweep = smem;
+	if (tpc_threads) {
+		smem_sweep = smem + hmp_dev_tpc_extra_smem(pl.scene_stride);
+		if (smem_sweep > ctx->max_smem_optin) {
+			tpc_threads = 0;
+			smem_sweep = smem;
+		}
+	}
 	int bps = 0;
-	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem, tpc_threads, &bps));
+	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, &bps));
 	else CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
@@ -653,6 +662,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	}
 	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes, sweep mode %d\n", smem, bps, per_scene, pl.n_scenes, tpc_threads);
 	if (sweep_mode_out) *sweep_mode_out = tpc_threads;
+	if (smem_sweep_out) *smem_sweep_out = smem_sweep;
 	*blocks_x_out = (int)per_scene;
 	*smem_out = smem;
 	*costmap_in_smem_out = in_smem;
@@ -1051,8 +1061,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	if ((rc = ctx->h_out.ensure(det_bytes + cl.total))) return rc;
 
 	int blocks_x = 0, in_smem = 0, sweep_mode = 0;
-	size_t smem = 0;
-	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem, &sweep_mode))) return rc;
+	size_t smem = 0, smem_sweep = 0;
+	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem, &sweep_mode, &smem_sweep))) return rc;
 	ctx->last_sweep_mode = sweep_mode;
 	if ((rc = ctx->d_block_best.ensure((size_t)NS * blocks_x * 2 * sizeof(unsigned long long)))) return rc;
 
@@ -1115,7 +1125,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
 		A.best_init = E.best_out;
 	}
-	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem, st));
+	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem_sweep, st));
 	ctx->launches++;
 	CU(cudaEventRecord(ctx->evm, st));
 	// snapshot the counters (n_generated, n_valid) before the detail pass reuses the work ticket

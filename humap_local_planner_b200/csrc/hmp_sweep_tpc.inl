@@ -23,12 +23,66 @@
 #define HMP_TPC_UNROLL 2
 #endif
 
+#ifndef HMP_TPC_PACKED
+#define HMP_TPC_PACKED 1   /* static-object loop in packed FP32x2 arithmetic (FFMA2 / FADD2 / FMUL2 of sm_100), two objects per iteration */
+#endif
+
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+// angle in [0, pi] of the vector (x, ay) with ay >= 0 and (x, ay) != (0, 0): atan2_r without the sign handling
+__device__ __forceinline__ float atan2_abs(float ay, float x) {
+	const float ax = fabsf(x);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	const float a = mn * rcp_ftz(mx);
+	const float t = a * a;
+	float p = 2.398139013e-03f;
+	p = fmaf(p, t, -1.415234804e-02f);
+	p = fmaf(p, t, 3.934541315e-02f);
+	p = fmaf(p, t, -7.194384543e-02f);
+	p = fmaf(p, t, 1.047753920e-01f);
+	p = fmaf(p, t, -1.415480604e-01f);
+	p = fmaf(p, t, 1.998488469e-01f);
+	p = fmaf(p, t, -3.333252400e-01f);
+	p = fmaf(p, t, 9.999998712e-01f);
+	float r = a * p;
+	if (ay > ax) r = 1.57079632679489662f - r;
+	if (x < 0.0f) r = PI_F - r;
+	return r;
+}
+
+// the same for two vectors at once in packed arithmetic (the polynomial is 8 FFMA2 instead of 16 FFMA)
+__device__ __forceinline__ float2 atan2_abs2(float2 ay, float2 x) {
+	const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+	const float2 mx = make_float2(fmaxf(ax.x, ay.x), fmaxf(ax.y, ay.y)), mn = make_float2(fminf(ax.x, ay.x), fminf(ax.y, ay.y));
+	const float2 a = __fmul2_rn(mn, make_float2(rcp_ftz(mx.x), rcp_ftz(mx.y)));
+	const float2 t = __fmul2_rn(a, a);
+	float2 p = bc2(2.398139013e-03f);
+	p = __ffma2_rn(p, t, bc2(-1.415234804e-02f));
+	p = __ffma2_rn(p, t, bc2(3.934541315e-02f));
+	p = __ffma2_rn(p, t, bc2(-7.194384543e-02f));
+	p = __ffma2_rn(p, t, bc2(1.047753920e-01f));
+	p = __ffma2_rn(p, t, bc2(-1.415480604e-01f));
+	p = __ffma2_rn(p, t, bc2(1.998488469e-01f));
+	p = __ffma2_rn(p, t, bc2(-3.333252400e-01f));
+	p = __ffma2_rn(p, t, bc2(9.999998712e-01f));
+	float2 r = __fmul2_rn(a, p);
+	if (ay.x > ax.x) r.x = 1.57079632679489662f - r.x;
+	if (ay.y > ax.y) r.y = 1.57079632679489662f - r.y;
+	if (x.x < 0.0f) r.x = PI_F - r.x;
+	if (x.y < 0.0f) r.y = PI_F - r.y;
+	return r;
+}
+
+#ifndef HMP_TPC_PAIR_UNROLL
+#define HMP_TPC_PAIR_UNROLL 1
+#endif
+
 __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_tpc_kernel(const KernelArgs A) {
 	using R = float;
 	using SC = float;
 	using TwistS = TwistT<float>;
 	constexpr int NW = HMP_TPC_THREADS / 32;
 	constexpr int TPC_UNROLL = HMP_TPC_UNROLL;   // static objects in flight per thread
+	[[maybe_unused]] constexpr int TPC_PAIR_UNROLL = HMP_TPC_PAIR_UNROLL;   // ... pairs of them in the packed loop
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t s_bar;
 	__shared__ double s_wbest[NW];
@@ -80,6 +134,27 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 	G.inv_res = P.inv_resolution;
 	G.sx = P.size_x;
 	G.sy = P.size_y;
+
+#if HMP_TPC_PACKED
+	// Static objects once more, as pairs of hi / lo floats (o = hi + lo to 2^-48): pair p = objects 2p, 2p + 1 as
+	// {xh0, xh1, yh0, yh1} {xl0, xl1, yl0, yl1}, so that one 16-byte broadcast load feeds the packed arithmetic of two objects
+	// and the difference to the robot position needs no FP64 subtraction and no conversion
+	const float4* pairs = reinterpret_cast<const float4*>(smem + ((L.total + 15u) & ~15u));
+	{
+		float* pf = reinterpret_cast<float*>(smem + ((L.total + 15u) & ~15u));
+		const int nsm = max(S.n_static0, S.n_static);
+		for (int j = tid; j < nsm; j += blockDim.x) {
+			const double2 o = reinterpret_cast<const double2*>(statics)[j];
+			const float xh = (float)o.x, yh = (float)o.y;
+			float* b = pf + (j >> 1) * 8 + (j & 1);
+			b[0] = xh;
+			b[2] = yh;
+			b[4] = (float)(o.x - (double)xh);
+			b[6] = (float)(o.y - (double)yh);
+		}
+	}
+	__syncthreads();
+#endif
 
 	const int T = P.T;
 	const float dt = P.dt;
@@ -224,8 +299,68 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 						fsy = fmaf(gmag, ey, fsy);
 					};
 					if (P.fov_method == 0) {
+						int j0 = 0;
+#if HMP_TPC_PACKED
+						if (forces_on) {
+							// ---- two objects per iteration in packed FP32x2 arithmetic; same formulas as static_body ----
+							const int npairs = ns >> 1;
+							const float rxh = (float)rxd, ryh = (float)ryd;
+							const float2 nrxh2 = bc2(-rxh), nryh2 = bc2(-ryh);
+							const float2 nrxl2 = bc2(-(float)(rxd - (double)rxh)), nryl2 = bc2(-(float)(ryd - (double)ryh));
+							const float2 yx2 = bc2(yx), yy2 = bc2(yy), nyl2_2 = bc2(-yl2);
+							// heading as a vector: the velocity, or the yaw direction for a (nearly) standing robot (world.cpp:26-30);
+							// the angle of an object relative to it is atan2(h x d, h . d), no wrap, and only its square is used
+							const bool moving = !(speed_d <= (SC)0.01);
+							const float2 hx2 = bc2(moving ? ux : c_r), hy2 = bc2(moving ? uy : s_r);
+							const float2 nhx2 = make_float2(-hx2.x, -hx2.y);
+							const float2 nbw2 = bc2(nbw_l2), fovn2 = bc2(fovn_l2), nawq2 = bc2(-0.25f * aw_g);
+							const float2 NHALF2 = bc2(-0.5f), C15_2 = bc2(1.5f), HALF2 = bc2(0.5f);
+							float2 fsx2 = make_float2(0.f, 0.f), fsy2 = make_float2(0.f, 0.f);
+							float dminp = CUDART_INF_F, gmin = CUDART_INF_F;
+#pragma unroll TPC_PAIR_UNROLL
+							for (int p = 0; p < npairs; ++p) {
+								const float4 a4 = pairs[2 * p], b4 = pairs[2 * p + 1];   // warp-uniform addresses: broadcast
+								const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(a4.x, a4.y), nrxh2), __fadd2_rn(make_float2(b4.x, b4.y), nrxl2));
+								const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(a4.z, a4.w), nryh2), __fadd2_rn(make_float2(b4.z, b4.w), nryl2));
+								const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+								const float2 bx = __fadd2_rn(dx, yx2), by = __fadd2_rn(dy, yy2);   // minus the scalar body's (bx, by)
+								const float2 b2 = __ffma2_rn(bx, bx, __fmul2_rn(by, by));
+								float2 ia = make_float2(rsqrt_ftz(d2.x), rsqrt_ftz(d2.y));
+								float2 ib = make_float2(rsqrt_ftz(b2.x), rsqrt_ftz(b2.y));
+								ia = __fmul2_rn(ia, __ffma2_rn(__fmul2_rn(__fmul2_rn(d2, NHALF2), ia), ia, C15_2));   // Newton step
+								ib = __fmul2_rn(ib, __ffma2_rn(__fmul2_rn(__fmul2_rn(b2, NHALF2), ib), ib, C15_2));
+								const float2 dist = __fmul2_rn(d2, ia), bl = __fmul2_rn(b2, ib);
+								const float2 sum = __fadd2_rn(dist, bl);
+								const float2 w2 = __ffma2_rn(sum, sum, nyl2_2);
+								float2 iw = make_float2(rsqrt_ftz(w2.x), rsqrt_ftz(w2.y));
+								iw = __fmul2_rn(iw, __ffma2_rn(__fmul2_rn(__fmul2_rn(w2, NHALF2), iw), iw, C15_2));
+								const float2 w = __fmul2_rn(__fmul2_rn(w2, iw), HALF2);
+								dminp = fminf(dminp, fminf(dist.x, dist.y));
+								// degenerate geometry (a zero-length vector, w ~ 0) is left to the scalar body: see below
+								gmin = fminf(gmin, fminf(fminf(fminf(d2.x, d2.y), fminf(b2.x, b2.y)), fminf(w2.x, w2.y)));
+								const float2 ex = __ffma2_rn(bx, ib, __fmul2_rn(dx, ia));   // minus the scalar body's (ex, ey)
+								const float2 ey = __ffma2_rn(by, ib, __fmul2_rn(dy, ia));
+								const float2 dot = __ffma2_rn(dx, hx2, __fmul2_rn(dy, hy2));
+								const float2 crs = __ffma2_rn(dx, hy2, __fmul2_rn(dy, nhx2));
+								const float2 ar = atan2_abs2(make_float2(fabsf(crs.x), fabsf(crs.y)), dot);
+								const float2 expo = __ffma2_rn(w, nbw2, __fmul2_rn(__fmul2_rn(ar, ar), fovn2));
+								const float2 e = make_float2(ex2_ftz(expo.x), ex2_ftz(expo.y));
+								const float2 ng = __fmul2_rn(__fmul2_rn(nawq2, e), __fmul2_rn(sum, w));   // -gmag
+								fsx2 = __ffma2_rn(ng, ex, fsx2);
+								fsy2 = __ffma2_rn(ng, ey, fsy2);
+							}
+							// every guard of the scalar body passes trivially when all squared lengths are above 1e-10; otherwise (or
+							// for NaN) this step's objects are done again by the scalar body
+							if (gmin > 1e-10f) {
+								j0 = 2 * npairs;
+								fsx = fsx2.x + fsx2.y;
+								fsy = fsy2.x + fsy2.y;
+								dmin = fminf(dmin, dminp);
+							}
+						}
+#endif
 #pragma unroll TPC_UNROLL
-						for (int j = 0; j < ns; ++j) static_body(std::true_type{}, j);
+						for (int j = j0; j < ns; ++j) static_body(std::true_type{}, j);
 					} else {
 #pragma unroll 1
 						for (int j = 0; j < ns; ++j) static_body(std::false_type{}, j);

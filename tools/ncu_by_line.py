@@ -1,6 +1,6 @@
 """Joins an `ncu --page source --csv` (per-SASS-instruction) dump with nvdisasm line info so that executed
 instructions and stall samples can be read per CUDA source line.
-usage: ncu_by_line.py <src.csv> <cubin> <kernel mangled substring> [top N]"""
+usage: ncu_by_line.py <src.csv> <cubin> <kernel mangled substring> [top N] [first line] [source file of the kernel body]"""
 import csv
 import re
 import subprocess
@@ -11,6 +11,7 @@ src_csv, cubin, kname = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 dis = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.splitlines()
 KERNEL_FIRST_LINE = int(sys.argv[5]) if len(sys.argv) > 5 else 0   # attribute to the outermost frame at/after this line
+KERNEL_FILE = sys.argv[6] if len(sys.argv) > 6 else "hmp_kernels.cu"   # file that holds the kernel body
 addr2line = {}
 frames = []
 last = None
@@ -28,7 +29,7 @@ for ln in dis:
     if m:
         pick = None
         for f, l in frames:            # innermost first; keep the outermost frame that lies in the kernel body
-            if f.endswith("hmp_kernels.cu") and l >= KERNEL_FIRST_LINE:
+            if f.endswith(KERNEL_FILE) and l >= KERNEL_FIRST_LINE:
                 pick = l
         if pick is None and frames:
             pick = frames[-1][1]
@@ -59,7 +60,7 @@ for r in rows[2:]:
     for s in stall_cols:
         stall[line][s] += f(r[ci[s]])
 ti, ts = sum(inst.values()), sum(samp.values())
-srclines = open("humap_local_planner_b200/csrc/hmp_kernels.cu").read().splitlines()
+srclines = open("humap_local_planner_b200/csrc/" + KERNEL_FILE).read().splitlines()
 print(f"total warp instructions {ti:.3e}, samples {ts:.0f}, mapped lines {len(inst)}")
 top = sorted(inst, key=lambda l: -samp[l])[:topn]
 for l in sorted(top):
