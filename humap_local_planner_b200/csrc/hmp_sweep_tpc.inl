@@ -28,50 +28,32 @@
 #endif
 
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
-// angle in [0, pi] of the vector (x, ay) with ay >= 0 and (x, ay) != (0, 0): atan2_r without the sign handling
-__device__ __forceinline__ float atan2_abs(float ay, float x) {
-	const float ax = fabsf(x);
-	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-	const float a = mn * rcp_ftz(mx);
-	const float t = a * a;
-	float p = 2.398139013e-03f;
-	p = fmaf(p, t, -1.415234804e-02f);
-	p = fmaf(p, t, 3.934541315e-02f);
-	p = fmaf(p, t, -7.194384543e-02f);
-	p = fmaf(p, t, 1.047753920e-01f);
-	p = fmaf(p, t, -1.415480604e-01f);
-	p = fmaf(p, t, 1.998488469e-01f);
-	p = fmaf(p, t, -3.333252400e-01f);
-	p = fmaf(p, t, 9.999998712e-01f);
-	float r = a * p;
-	if (ay > ax) r = 1.57079632679489662f - r;
-	if (x < 0.0f) r = PI_F - r;
+// Angle in [0, pi] between two vectors from the cosine c and the (non-negative) sine s of it, both for two vectors at once
+// in packed arithmetic, without a division: asin of the smaller of (s, |c|) by a degree-7 minimax polynomial in z^2 on
+// [0, sin(pi/4)] (max error 9e-8 in FP32 evaluation, the accuracy class of atan2_r), then the octant.
+__device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
+	const bool lo_x = s.x <= fabsf(c.x), lo_y = s.y <= fabsf(c.y);
+	const float2 z = make_float2(lo_x ? s.x : c.x, lo_y ? s.y : c.y);
+	const float2 q = __fmul2_rn(z, z);
+	float2 p = bc2(1.448995462e-01f);
+	p = __ffma2_rn(p, q, bc2(-1.801251085e-01f));
+	p = __ffma2_rn(p, q, bc2(1.457034517e-01f));
+	p = __ffma2_rn(p, q, bc2(-2.460549290e-02f));
+	p = __ffma2_rn(p, q, bc2(4.040429929e-02f));
+	p = __ffma2_rn(p, q, bc2(4.341339492e-02f));
+	p = __ffma2_rn(p, q, bc2(7.508057529e-02f));
+	p = __ffma2_rn(p, q, bc2(1.666642890e-01f));
+	p = __ffma2_rn(p, q, bc2(1.000000020e+00f));
+	float2 r = __fmul2_rn(z, p);   // asin(z), signed
+	// s <= |c|: the angle is asin(s) in front (c >= 0) and pi - asin(s) behind; otherwise acos(c) = pi/2 - asin(c)
+	r.x = lo_x ? ((c.x < 0.0f) ? PI_F - r.x : r.x) : 1.57079632679489662f - r.x;
+	r.y = lo_y ? ((c.y < 0.0f) ? PI_F - r.y : r.y) : 1.57079632679489662f - r.y;
 	return r;
 }
 
-// the same for two vectors at once in packed arithmetic (the polynomial is 8 FFMA2 instead of 16 FFMA)
-__device__ __forceinline__ float2 atan2_abs2(float2 ay, float2 x) {
-	const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-	const float2 mx = make_float2(fmaxf(ax.x, ay.x), fmaxf(ax.y, ay.y)), mn = make_float2(fminf(ax.x, ay.x), fminf(ax.y, ay.y));
-	const float2 a = __fmul2_rn(mn, make_float2(rcp_ftz(mx.x), rcp_ftz(mx.y)));
-	const float2 t = __fmul2_rn(a, a);
-	float2 p = bc2(2.398139013e-03f);
-	p = __ffma2_rn(p, t, bc2(-1.415234804e-02f));
-	p = __ffma2_rn(p, t, bc2(3.934541315e-02f));
-	p = __ffma2_rn(p, t, bc2(-7.194384543e-02f));
-	p = __ffma2_rn(p, t, bc2(1.047753920e-01f));
-	p = __ffma2_rn(p, t, bc2(-1.415480604e-01f));
-	p = __ffma2_rn(p, t, bc2(1.998488469e-01f));
-	p = __ffma2_rn(p, t, bc2(-3.333252400e-01f));
-	p = __ffma2_rn(p, t, bc2(9.999998712e-01f));
-	float2 r = __fmul2_rn(a, p);
-	if (ay.x > ax.x) r.x = 1.57079632679489662f - r.x;
-	if (ay.y > ax.y) r.y = 1.57079632679489662f - r.y;
-	if (x.x < 0.0f) r.x = PI_F - r.x;
-	if (x.y < 0.0f) r.y = PI_F - r.y;
-	return r;
-}
-
+#ifndef HMP_TPC_STRIDED
+#define HMP_TPC_STRIDED 1
+#endif
 #ifndef HMP_TPC_PAIR_UNROLL
 #define HMP_TPC_PAIR_UNROLL 1
 #endif
@@ -173,7 +155,17 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 		if (tid == 0) s_base = (int)atomicAdd(&counters[0], blockDim.x);   // a block may be launched with fewer than HMP_TPC_THREADS threads
 		__syncthreads();
 		if (s_base >= A.n_work) break;
+#if HMP_TPC_STRIDED
+		// Ticket k gives warp w the 32 candidates of chunk w * n_tickets + k: the warps of a block (and so of an SM) take
+		// chunks spread evenly over the whole sampling grid instead of consecutive ones. Neighbouring candidates cost about the
+		// same (they differ in the innermost amplifiers), so consecutive chunks make whole blocks cheap or expensive and the
+		// single wave of blocks ends with the most expensive SM; the lanes of a warp still hold consecutive candidates.
+		const int nwb = (int)(blockDim.x >> 5);
+		const int n_tickets = ((A.n_work + 31) / 32 + nwb - 1) / nwb;
+		const int wk = (warp * n_tickets + s_base / (int)blockDim.x) * 32 + lane;
+#else
 		const int wk = s_base + tid;
+#endif
 		const bool active = wk < A.n_work;
 		const int cand = active ? wk + A.cand_offset : 0;
 
@@ -313,6 +305,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 							const bool moving = !(speed_d <= (SC)0.01);
 							const float2 hx2 = bc2(moving ? ux : c_r), hy2 = bc2(moving ? uy : s_r);
 							const float2 nhx2 = make_float2(-hx2.x, -hx2.y);
+							const float2 ih2 = bc2(moving ? (SC)1 / speed_d : (SC)1);   // 1 / |h|
 							const float2 nbw2 = bc2(nbw_l2), fovn2 = bc2(fovn_l2), nawq2 = bc2(-0.25f * aw_g);
 							const float2 NHALF2 = bc2(-0.5f), C15_2 = bc2(1.5f), HALF2 = bc2(0.5f);
 							float2 fsx2 = make_float2(0.f, 0.f), fsy2 = make_float2(0.f, 0.f);
@@ -342,7 +335,9 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 								const float2 ey = __ffma2_rn(by, ib, __fmul2_rn(dy, ia));
 								const float2 dot = __ffma2_rn(dx, hx2, __fmul2_rn(dy, hy2));
 								const float2 crs = __ffma2_rn(dx, hy2, __fmul2_rn(dy, nhx2));
-								const float2 ar = atan2_abs2(make_float2(fabsf(crs.x), fabsf(crs.y)), dot);
+								const float2 ihd = __fmul2_rn(ia, ih2);
+								const float2 cs2 = __fmul2_rn(dot, ihd), sn2 = __fmul2_rn(make_float2(fabsf(crs.x), fabsf(crs.y)), ihd);
+								const float2 ar = angle_from_cos_sin2(cs2, sn2);
 								const float2 expo = __ffma2_rn(w, nbw2, __fmul2_rn(__fmul2_rn(ar, ar), fovn2));
 								const float2 e = make_float2(ex2_ftz(expo.x), ex2_ftz(expo.y));
 								const float2 ng = __fmul2_rn(__fmul2_rn(nawq2, e), __fmul2_rn(sum, w));   // -gmag

@@ -415,11 +415,12 @@ def test_sweep_layouts_agree(planner, name, seed):
             planner.set_precision(False)
         out[lay] = (res, tot, ref)
     (ra, ta, fa), (rb, tb, fb) = out[1], out[2]
-    assert ra.n_candidates == rb.n_candidates and ra.n_generated == rb.n_generated
+    assert ra.n_candidates == rb.n_candidates
+    assert abs(ra.n_generated - rb.n_generated) <= max(1, 0.001 * ra.n_candidates)   # borderline feasibility tests
     same_sign = (ta < 0) == (tb < 0)
     assert same_sign.mean() >= 0.999
     neg = (ta < 0) & (tb < 0)
-    assert np.array_equal(ta[neg], tb[neg])
+    assert (ta[neg] == tb[neg]).mean() >= 0.999    # -1 (generator rejected) vs -6 for borderline feasibility tests
     assert abs(ra.n_valid - rb.n_valid) <= max(1, 0.001 * ra.n_candidates)
     v = (ta >= 0) & (tb >= 0)
     rel = _rel_err(ta[v], tb[v])
