@@ -607,7 +607,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	size_t cm_bytes = (size_t)ctx->costmap_stride;
 	int in_smem = 1;
 	size_t smem = hmp_dev_smem_bytes(pl.scene_stride, (uint32_t)cm_bytes, 1);
-	if (smem > ctx->max_smem_optin || cm_bytes > (1u << 19)) {
+	if (smem > ctx->max_smem_optin || cm_bytes > (1u << 19) || getenv("HMP_CM_GLOBAL")) {   // HMP_CM_GLOBAL=1: A/B of the global-memory costmap path
 		in_smem = 0;
 		smem = hmp_dev_smem_bytes(pl.scene_stride, (uint32_t)cm_bytes, 0);
 		if (smem > ctx->max_smem_optin) {

@@ -51,6 +51,9 @@ __device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
 	return r;
 }
 
+#ifndef HMP_TPC_LOCKSTEP
+#define HMP_TPC_LOCKSTEP 0
+#endif
 #ifndef HMP_TPC_STRIDED
 #define HMP_TPC_STRIDED 1
 #endif
@@ -58,7 +61,10 @@ __device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
 #define HMP_TPC_PAIR_UNROLL 1
 #endif
 
-__global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_tpc_kernel(const KernelArgs A) {
+#ifndef HMP_TPC_MIN_BLOCKS
+#define HMP_TPC_MIN_BLOCKS (512 / HMP_TPC_THREADS)
+#endif
+__global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc_kernel(const KernelArgs A) {
 	using R = float;
 	using SC = float;
 	using TwistS = TwistT<float>;
@@ -229,7 +235,12 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, 512 / HMP_TPC_THREADS) sweep_
 
 		for (int i = 0; i < T; ++i) {
 			bool alive = active && !rejected;
+#if HMP_TPC_LOCKSTEP
+			__syncthreads();   // the warps of a block walk the horizon together: the step body streams through the instruction caches once per block-step
+			if (!__any_sync(0xffffffffu, alive)) continue;
+#else
 			if (!__any_sync(0xffffffffu, alive)) break;   // warp-uniform
+#endif
 			double cd = 1.0, sd = 0.0;
 			TwistS tw = {0, 0, 0};
 			SC tgx_d = 0, tgy_d = 0;
