@@ -51,6 +51,67 @@ __device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
 	return r;
 }
 
+struct PeopleMax {
+	float hd, psi, ps;
+};
+// People critics of one pose with the literal per-step person pose (people with a yaw rate): heading disturbance
+// (heading_disturbance_cost_function.cpp:69-86), personal space (personal_space_intrusion_cost_function.cpp:55-78), passing
+// speed (passing_speed_cost_function.cpp:57-71). Same statements as the people loop of plan_kernel.
+__device__ __noinline__ PeopleMax people_critics_generic(const DevPerson* people, int n_people, float tp, float rx, float ry, float rspeed,
+                                                         float motion_dir, float sp_norm, bool do_psi, bool do_hd, bool do_ps,
+                                                         float hd_neg_inv_2var_fov, float hd_inv_max_speed, float hd_dmin, float ps_min_dist,
+                                                         PeopleMax m) {
+#pragma unroll 1
+	for (int p = 0; p < n_people; ++p) {
+		const float4 a0 = reinterpret_cast<const float4*>(people)[4 * p];
+		const float4 a1 = reinterpret_cast<const float4*>(people)[4 * p + 1];
+		const float4 a2 = reinterpret_cast<const float4*>(people)[4 * p + 2];
+		const float4 a3 = reinterpret_cast<const float4*>(people)[4 * p + 3];
+		float pxp = fmaf(tp, a1.x, a0.x), pyp = fmaf(tp, a1.y, a0.y);
+		float dx = rx - pxp, dy = ry - pyp;
+		float dist = sqrt_nr(dx * dx + dy * dy);
+		float yawp = a0.z, cp = a1.z, sp = a1.w;
+		if (a0.w != 0.0f) {   // warp-uniform (a property of the person)
+			yawp = wrapf(fmaf(tp, a0.w, a0.z));
+			sincosf(yawp, &sp, &cp);
+		}
+		if (do_psi) {
+			// personal_space_intrusion_cost_function.cpp:55-78 (asymmetric Gaussian, peak 1)
+			float along = dx * cp + dy * sp;
+			float vh = (along >= 0.0f) ? a3.x : a3.y;
+			float vs = a3.z;
+			float ga = vh * cp * cp + vs * sp * sp + a2.x;
+			float gb = (vh - vs) * cp * sp;
+			float gc = vh * sp * sp + vs * cp * cp + a2.w;
+			float b1 = gb + a2.y, b2 = gb + a2.z;
+			float det = ga * gc - b1 * b2;
+			float q = (gc * dx * dx - (b1 + b2) * dx * dy + ga * dy * dy) / det;
+			m.psi = fmaxf(m.psi, __expf(-0.5f * q));
+		}
+		if (do_hd) {
+			// heading_disturbance_cost_function.cpp:69-86
+			float v = 0.0f;
+			if (!(rspeed < 1e-9f) && !(dist < 1e-9f)) {
+				float dist_angle = atan2_r(dy, dx);
+				float rel_loc = wrapf(dist_angle - yawp);
+				float gamma_cc = wrapf(dist_angle + PI_F);
+				float half = atan2_r(a3.w, dist);
+				float dd = wrapf(motion_dir - gamma_cc);
+				float g_dir = __expf(-(dd * dd) / (2.0f * half * half));
+				float g_fov = __expf(rel_loc * rel_loc * hd_neg_inv_2var_fov);
+				v = g_dir * g_fov * (rspeed * hd_inv_max_speed) * (hd_dmin / fmaxf(dist, hd_dmin));
+			}
+			m.hd = fmaxf(m.hd, v);
+		}
+		if (do_ps) {
+			// passing_speed_cost_function.cpp:57-71
+			float clearance = fmaxf(dist - ps_min_dist, 0.0f);
+			m.ps = fmaxf(m.ps, sp_norm * __expf(-clearance));
+		}
+	}
+	return m;
+}
+
 #ifndef HMP_TPC_LOCKSTEP
 #define HMP_TPC_LOCKSTEP 0
 #endif
@@ -143,6 +204,44 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 	}
 	__syncthreads();
 #endif
+
+	// People whose yaw does not change over the horizon (yaw rate 0: what the people tracker delivers) have a personal-space
+	// Gaussian that depends on the candidate only through the SIDE the robot is on (front / rear variance): the quadratic
+	// form q = A dx^2 + B dx dy + C dy^2 of both sides is worked out once per block and written over the person's record
+	// (same 64 bytes: {x, y, vx, vy} {cos, sin, radius_eff, 0} {A, B, C front, 0} {A, B, C rear, 0}). One person with a yaw rate
+	// keeps the literal per-step evaluation for everybody.
+	__shared__ int s_yaw_rate;
+	if (tid == 0) s_yaw_rate = 0;
+	__syncthreads();
+	for (int p = tid; p < S.n_people; p += blockDim.x)
+		if (people[p].vth != 0.0f) atomicOr(&s_yaw_rate, 1);
+	__syncthreads();
+	const bool people_tab = (s_yaw_rate == 0);
+	if (people_tab) {
+		float4* pt = reinterpret_cast<float4*>(const_cast<unsigned char*>(blob + S.off_people));
+		for (int p = tid; p < S.n_people; p += blockDim.x) {
+			const DevPerson q = people[p];
+			float abc[2][3];
+#pragma unroll
+			for (int side = 0; side < 2; ++side) {
+				// personal_space_intrusion_cost_function.cpp:55-78: heading variance by side + side variance, rotated, + pose covariance
+				const float vh = side ? q.var_rear : q.var_front, vs = q.var_side, cp = q.cos0, sp = q.sin0;
+				const float ga = vh * cp * cp + vs * sp * sp + q.cxx;
+				const float gb = (vh - vs) * cp * sp;
+				const float gc = vh * sp * sp + vs * cp * cp + q.cyy;
+				const float b1 = gb + q.cxy, b2 = gb + q.cyx;
+				const float det = ga * gc - b1 * b2;
+				abc[side][0] = gc / det;
+				abc[side][1] = -(b1 + b2) / det;
+				abc[side][2] = ga / det;
+			}
+			pt[4 * p + 0] = make_float4(q.x, q.y, q.vx, q.vy);
+			pt[4 * p + 1] = make_float4(q.cos0, q.sin0, q.radius_eff, 0.0f);
+			pt[4 * p + 2] = make_float4(abc[0][0], abc[0][1], abc[0][2], 0.0f);
+			pt[4 * p + 3] = make_float4(abc[1][0], abc[1][1], abc[1][2], 0.0f);
+		}
+	}
+	__syncthreads();
 
 	const int T = P.T;
 	const float dt = P.dt;
@@ -617,53 +716,55 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 						const float rspeed = hypotf(tgx_d, tgy_d);
 						const float motion_dir = atan2_r(tgy_d, tgx_d);
 						const float sp_norm = fminf(fmaxf(rspeed * P.ps_inv_max_speed, 0.0f), 1.0f);
+						if (people_tab) {
+							// table path (all yaw rates zero). The heading-disturbance critic needs two angles only as squares: the
+							// robot relative to the person's heading and the robot's motion direction relative to the direction
+							// robot -> person; both come from their cosine and |sine| (dot / cross products over the distance) in ONE
+							// packed evaluation, instead of two atan2 and three wraps
+							const bool hd_ok = do_hd && !(rspeed < 1e-9f);
+							const float inv_rs = hd_ok ? 1.0f / rspeed : 0.0f;
+							const float mxu = tgx_d * inv_rs, myu = tgy_d * inv_rs;   // unit motion direction
+							const float hd_speed = rspeed * P.hd_inv_max_speed;
+							const float4* pt = reinterpret_cast<const float4*>(people);
 #pragma unroll 1
-						for (int p = 0; p < S.n_people; ++p) {
-							const float4 a0 = reinterpret_cast<const float4*>(people)[4 * p];
-							const float4 a1 = reinterpret_cast<const float4*>(people)[4 * p + 1];
-							const float4 a2 = reinterpret_cast<const float4*>(people)[4 * p + 2];
-							const float4 a3 = reinterpret_cast<const float4*>(people)[4 * p + 3];
-							float pxp = fmaf(tp, a1.x, a0.x), pyp = fmaf(tp, a1.y, a0.y);
-							float dx = rx - pxp, dy = ry - pyp;
-							float dist = sqrt_nr(dx * dx + dy * dy);
-							float yawp = a0.z, cp = a1.z, sp = a1.w;
-							if (a0.w != 0.0f) {   // warp-uniform (a property of the person)
-								yawp = wrapf(fmaf(tp, a0.w, a0.z));
-								sincosf(yawp, &sp, &cp);
-							}
-							if (do_psi) {
-								// personal_space_intrusion_cost_function.cpp:55-78 (asymmetric Gaussian, peak 1)
-								float along = dx * cp + dy * sp;
-								float vh = (along >= 0.0f) ? a3.x : a3.y;
-								float vs = a3.z;
-								float ga = vh * cp * cp + vs * sp * sp + a2.x;
-								float gb = (vh - vs) * cp * sp;
-								float gc = vh * sp * sp + vs * cp * cp + a2.w;
-								float b1 = gb + a2.y, b2 = gb + a2.z;
-								float det = ga * gc - b1 * b2;
-								float q = (gc * dx * dx - (b1 + b2) * dx * dy + ga * dy * dy) / det;
-								psi_max = fmaxf(psi_max, __expf(-0.5f * q));
-							}
-							if (do_hd) {
-								// heading_disturbance_cost_function.cpp:69-86
-								float v = 0.0f;
-								if (!(rspeed < 1e-9f) && !(dist < 1e-9f)) {
-									float dist_angle = atan2_r(dy, dx);
-									float rel_loc = wrapf(dist_angle - yawp);
-									float gamma_cc = wrapf(dist_angle + PI_F);
-									float half = atan2_r(a3.w, dist);
-									float dd = wrapf(motion_dir - gamma_cc);
-									float g_dir = __expf(-(dd * dd) / (2.0f * half * half));
-									float g_fov = __expf(rel_loc * rel_loc * P.hd_neg_inv_2var_fov);
-									v = g_dir * g_fov * (rspeed * P.hd_inv_max_speed) * (P.hd_dmin / fmaxf(dist, P.hd_dmin));
+							for (int p = 0; p < S.n_people; ++p) {
+								const float4 t0 = pt[4 * p], t1 = pt[4 * p + 1];   // warp-uniform addresses: broadcast
+								const float dx = rx - fmaf(tp, t0.z, t0.x), dy = ry - fmaf(tp, t0.w, t0.y);
+								float dist, inv;
+								len_inv(dx * dx + dy * dy, dist, inv);
+								const float along = dx * t1.x + dy * t1.y;
+								if (do_psi) {
+									const float4 tq = (along >= 0.0f) ? pt[4 * p + 2] : pt[4 * p + 3];
+									const float q = tq.x * dx * dx + tq.y * dx * dy + tq.z * dy * dy;
+									psi_max = fmaxf(psi_max, __expf(-0.5f * q));
 								}
-								hd_max = fmaxf(hd_max, v);
+								if (do_hd) {
+									float v = 0.0f;
+									if (hd_ok && !(dist < 1e-9f)) {
+										const float crs = t1.x * dy - t1.y * dx;
+										const float dotm = -(mxu * dx + myu * dy), crsm = mxu * dy - myu * dx;
+										const float2 ang = angle_from_cos_sin2(__fmul2_rn(make_float2(along, dotm), bc2(inv)),
+										                                       __fmul2_rn(make_float2(fabsf(crs), fabsf(crsm)), bc2(inv)));
+										const float half = atan2_r(t1.z, dist);
+										const float g_dir = __expf(-0.5f * (ang.y * ang.y) * rcp_ftz(half * half));
+										const float g_fov = __expf(ang.x * ang.x * P.hd_neg_inv_2var_fov);
+										v = g_dir * g_fov * hd_speed * fminf(1.0f, P.hd_dmin * inv);
+									}
+									hd_max = fmaxf(hd_max, v);
+								}
+								if (do_ps) {
+									const float clearance = fmaxf(dist - P.ps_min_dist, 0.0f);
+									ps_max = fmaxf(ps_max, sp_norm * __expf(-clearance));
+								}
 							}
-							if (do_ps) {
-								// passing_speed_cost_function.cpp:57-71
-								float clearance = fmaxf(dist - P.ps_min_dist, 0.0f);
-								ps_max = fmaxf(ps_max, sp_norm * __expf(-clearance));
-							}
+						} else {
+							// somebody turns: the literal per-step evaluation, out of line (rare path, keeps its registers out of the sweep)
+							const PeopleMax pm = people_critics_generic(people, S.n_people, tp, rx, ry, rspeed, motion_dir, sp_norm, do_psi, do_hd,
+							                                            do_ps, P.hd_neg_inv_2var_fov, P.hd_inv_max_speed, P.hd_dmin, P.ps_min_dist,
+							                                            PeopleMax{hd_max, psi_max, ps_max});
+							hd_max = pm.hd;
+							psi_max = pm.psi;
+							ps_max = pm.ps;
 						}
 					}
 				}

@@ -486,6 +486,12 @@ def _m_no_people(p, sc):
     sc.world.n_obstacles = 30
 
 
+def _m_turning_people(p, sc):
+    # people with a yaw rate: the per-step person pose (trajectory.h:160-193) instead of the per-block personal-space table
+    for i in range(sc.world.n_people):
+        sc.world.people[i].vth = 0.4 if i % 2 else -0.25
+
+
 def _m_empty_world(p, sc):
     sc.world.n_people = sc.world.n_groups = sc.world.n_obstacles = 0
 
@@ -501,7 +507,7 @@ def _m_near_edge(p, sc):
 
 VARIANTS = [_m_fis_off, _m_filter, _m_linear_fov, _m_maintain, _m_ttc_rollout, _m_sum_cross, _m_first_step_only,
             _m_stop_on_failure, _m_disable_interaction, _m_zero_scales, _m_no_people, _m_empty_world, _m_short_horizon,
-            _m_near_edge]
+            _m_near_edge, _m_turning_people]
 
 
 @pytest.mark.parametrize("precise", [True, False], ids=["fp64", "fp32"])
