@@ -205,6 +205,14 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 	__syncthreads();
 #endif
 
+	// Dynamic objects: dir_beta and speed are only ever read as floats, the velocity as both: their float copies
+	// {dir_beta, speed, vx, vy} go over the last 16 bytes of the record (the double `speed` and the padding), saving four
+	// conversions per object-step
+	for (int k = tid; k < max(S.n_dynamic, S.n_dynamic_later); k += blockDim.x) {
+		const DevDynamic o = dynamics[k];
+		float4* w = reinterpret_cast<float4*>(const_cast<DevDynamic*>(dynamics + k)) + 3;
+		*w = make_float4((float)o.dir_beta, (float)o.speed, (float)o.vx, (float)o.vy);
+	}
 	// People whose yaw does not change over the horizon (yaw rate 0: what the people tracker delivers) have a personal-space
 	// Gaussian that depends on the candidate only through the SIDE the robot is on (front / rear variance): the quadratic
 	// form q = A dx^2 + B dx dy + C dy^2 of both sides is worked out once per block and written over the person's record
@@ -331,6 +339,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 		const R neg_inv_Bw = -1.0f / Bw;
 		const R nbw_l2 = neg_inv_Bw * 1.4426950408889634f, fovn_l2 = fovn * 1.4426950408889634f;
 		const R aw_g = Aw * fovg;
+		constexpr R L2E = 1.4426950408889634f;
+		const R nBn_l2 = -Bn * L2E, Cn_l2 = Cn * L2E, nBp_l2 = -Bp * L2E, Cp_l2 = Cp * L2E;
 
 		for (int i = 0; i < T; ++i) {
 			bool alive = active && !rejected;
@@ -489,14 +499,17 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 						R arel = fabsf(rel);
 						R side = (arel <= nine || arel >= Cst<R>::pi() - nine) ? (R)0 : ((rel <= (R)0) ? (R)-1 : (R)1);
 						R rel_loc = wrapf(rel);
+						const float4 of = reinterpret_cast<const float4*>(&o)[3];   // {dir_beta, speed, vx, vy} as floats (prologue)
 						if (dist <= (R)7.5) {
-							R vrx = (R)o.vx - ux, vry = (R)o.vy - uy;
-							R vrel = sqrtf(vrx * vrx + vry * vry);
+							R vrx = of.z - ux, vry = of.w - uy;
+							R vrel, inv_vrel;
+							len_inv(vrx * vrx + vry * vry, vrel, inv_vrel);
 							if (vrel >= (R)1e-6) {
-								R fov = fov_factor<R>(rel_loc, P.fov_method, fovh, fovg, fovn);
+								R fov = (P.fov_method == 0) ? fovg * ex2_ftz(rel_loc * rel_loc * fovn_l2) : fov_factor<R>(rel_loc, 1, fovh, fovg, fovn);
 								R thab = wrapf(th_r - angle_d);
-								R en = An * expf(((-Bn * thab * thab) / vrel) - Cn * dist) * fov;
-								R ep = Ap * expf(((-Bp * fabsf(thab)) / vrel) - Cp * dist) * fov * side;
+								// exponentials as ex2 of pre-scaled arguments (as in the static loop), the two divisions by vrel as one reciprocal
+								R en = An * ex2_ftz(((nBn_l2 * thab * thab) * inv_vrel) - Cn_l2 * dist) * fov;
+								R ep = Ap * ex2_ftz(((nBp_l2 * fabsf(thab)) * inv_vrel) - Cp_l2 * dist) * fov * side;
 								// n = (c, s); p = side * (s, -c)  (LEFT: n x z, RIGHT: n x -z)
 								fdx_r += c_r * en + s_r * ep;
 								fdy_r += s_r * en - c_r * ep;
@@ -504,14 +517,14 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 						}
 						if (P.fis_on && dist <= (R)P.fis_range_d) {
 							// social_conductor.cpp:37-105, :162-179
-							R strength = (expf(speed_r + (R)o.speed) - (R)1) * expf(-dist);
+							R strength = (ex2_ftz((speed_r + of.y) * L2E) - (R)1) * ex2_ftz(-dist * L2E);
 							R val, mu;
-							fis_process<R>(heading_r, (R)o.dir_beta, rel_loc, angle_d, val, mu);
+							fis_process<R>(heading_r, of.x, rel_loc, angle_d, val, mu);
 							if (mu > (R)0) {
 								R ff = (R)1;
-								if (P.fis_fov_method == 0 || P.fis_fov_method == 1)
-									ff = fov_factor<R>(rel_loc, P.fis_fov_method, (R)P.fis_fov_half_d, (R)P.fis_gauss_scale_d,
-									                   (R)P.fis_neg_inv_2var_d);
+								if (P.fis_fov_method == 0) ff = (R)P.fis_gauss_scale_d * ex2_ftz(rel_loc * rel_loc * ((R)P.fis_neg_inv_2var_d * L2E));
+								else if (P.fis_fov_method == 1)
+									ff = fov_factor<R>(rel_loc, 1, (R)P.fis_fov_half_d, (R)P.fis_gauss_scale_d, (R)P.fis_neg_inv_2var_d);
 								R mag = As * mu * strength * ff;
 								R sv, cv;
 								sincosf(val, &sv, &cv);
