@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 		const DevDynamic o = dynamics[k];
 		float4* w = reinterpret_cast<float4*>(const_cast<DevDynamic*>(dynamics + k)) + 3;
 		*w = make_float4((float)o.dir_beta, (float)o.speed, (float)o.vx, (float)o.vy);
+		reinterpret_cast<float2*>(const_cast<DevDynamic*>(dynamics + k))[4] = make_float2((float)o.psi0, 0.0f);   // over the double psi0
 	}
 	// People whose yaw does not change over the horizon (yaw rate 0: what the people tracker delivers) have a personal-space
 	// Gaussian that depends on the candidate only through the SIDE the robot is on (front / rear variance): the quadratic
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 			if (alive) {
 				sincos(th, &sd, &cd);
 				const double rxd = x - S.x0, ryd = y - S.y0;
-				const double dpsi = th - S.yaw0;
+				const float dpsi_f = (float)(th - S.yaw0);
 				const double tnow = (double)i * P.dt_d;
 				// -- derived robot data (world.cpp:20-33) --
 				const SC speed_d = sqrt_s(ux * ux + uy * uy);
@@ -493,13 +494,15 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 						R dist = sqrt_nr(dx * dx + dy * dy);
 						dmin = fminf(dmin, dist);
 						if (!forces_on) continue;
+						const float4 of = reinterpret_cast<const float4*>(&o)[3];   // {dir_beta, speed, vx, vy} as floats (prologue)
+						const float opsi = reinterpret_cast<const float2*>(&o)[4].x;   // psi0 as a float (prologue)
 						// World::computeObjectRelativeLocation, world.cpp:192-229 (un-normalised difference)
 						R angle_d = atan2_r(dy, dx);
-						R rel = angle_d - (R)wrapd(o.psi0 + dpsi);
+						R rel = angle_d - wrapf(opsi + dpsi_f);   // FP32 here (the FP64 wrap was 50 cycles of dependent latency per object)
 						R arel = fabsf(rel);
 						R side = (arel <= nine || arel >= Cst<R>::pi() - nine) ? (R)0 : ((rel <= (R)0) ? (R)-1 : (R)1);
 						R rel_loc = wrapf(rel);
-						const float4 of = reinterpret_cast<const float4*>(&o)[3];   // {dir_beta, speed, vx, vy} as floats (prologue)
+
 						if (dist <= (R)7.5) {
 							R vrx = of.z - ux, vry = of.w - uy;
 							R vrel, inv_vrel;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 									ff = fov_factor<R>(rel_loc, 1, (R)P.fis_fov_half_d, (R)P.fis_gauss_scale_d, (R)P.fis_neg_inv_2var_d);
 								R mag = As * mu * strength * ff;
 								R sv, cv;
-								sincosf(val, &sv, &cv);
+								__sincosf(val, &sv, &cv);   // |val| <= pi: 4e-7 absolute, below the error of the centroid itself
 								fhx = fmaf(mag, cv, fhx);
 								fhy = fmaf(mag, sv, fhy);
 							}
