@@ -1094,6 +1094,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.counters = (unsigned int*)(ctrl + cl.off_counters);
 	A.hv_out = (unsigned int*)(ctrl + cl.off_hv);
 	A.best_out = (double*)(ctrl + cl.off_best);
+	A.no_prune = ctx->prune_obstacle ? 0 : 1;
 
 	CU(cudaEventRecord(ctx->ev0, st));
 	// dilated max-cost map for the exact pruning of the obstacle critic (rebuilt when costmap / footprint / separation change)

@@ -190,7 +190,7 @@ struct KernelArgs {
 	                                    cell the footprint critic can touch from a centre in that cell (255 outside the map), or
 	                                    null: lets the obstacle critic skip poses that cannot raise its running maximum        */
 	int32_t cand_offset;             /* sweep launches: candidate = work index + cand_offset (the equisampled sweep starts at n_social) */
-	int32_t _pado;
+	int32_t no_prune;                /* 1: the exact prunings of the max-type critics (obstacle: dilated map, people: distance bounds) are off (A/B) */
 	const double* best_init;         /* [n_scenes][2] (total, index) of an earlier sweep over other candidates of the same pool, merged
 	                                    into best_out by the last block (ties: lower index wins), or null                */
 	int32_t forces_only;             /* detail launches of the force-field grid: rollout arithmetic only, no critic touches the costmap / MapGrids */

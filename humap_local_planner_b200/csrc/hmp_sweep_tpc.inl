@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 				abc[side][2] = ga / det;
 			}
 			pt[4 * p + 0] = make_float4(q.x, q.y, q.vx, q.vy);
-			pt[4 * p + 1] = make_float4(q.cos0, q.sin0, q.radius_eff, 0.0f);
+			// largest eigenvalue of either side's covariance is below this: q >= |d|^2 / lam, the bound the exact pruning uses
+			const float lam = fmaxf(fmaxf(q.var_front, q.var_rear), q.var_side) + fabsf(q.cxx) + fabsf(q.cyy) + fabsf(q.cxy) + fabsf(q.cyx);
+			pt[4 * p + 1] = make_float4(q.cos0, q.sin0, q.radius_eff, 0.5f * 1.4426950408889634f / lam);
 			pt[4 * p + 2] = make_float4(abc[0][0], abc[0][1], abc[0][2], 0.0f);
 			pt[4 * p + 3] = make_float4(abc[1][0], abc[1][1], abc[1][2], 0.0f);
 		}
@@ -748,13 +750,26 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 								const float dx = rx - fmaf(tp, t0.z, t0.x), dy = ry - fmaf(tp, t0.w, t0.y);
 								float dist, inv;
 								len_inv(dx * dx + dy * dy, dist, inv);
+								// Exact pruning (both critics are maxima over people and poses): the personal-space value is at most
+								// exp(-|d|^2 / (2 lam)) and the heading disturbance at most speed x min(1, dmin / |d|); a person whose
+								// bounds (with 1e-4 of slack for the FP32 evaluation) do not exceed the running maxima cannot change
+								// them. The lanes of a warp are neighbours in the sampling grid, so they mostly agree and the warp skips.
+								const float d2p = dx * dx + dy * dy;
+								const bool psi_live = do_psi && (ex2_ftz(-d2p * t1.w) * 1.0001f > psi_max || A.no_prune);
+								const float hd_bound = hd_speed * fminf(1.0f, P.hd_dmin * inv);
+								const bool hd_live = do_hd && (hd_bound * 1.0001f > hd_max || !(hd_max >= 0.0f) || A.no_prune);
+								if (do_ps) {
+									const float clearance = fmaxf(dist - P.ps_min_dist, 0.0f);
+									ps_max = fmaxf(ps_max, sp_norm * __expf(-clearance));
+								}
+								if (!(psi_live || hd_live)) continue;
 								const float along = dx * t1.x + dy * t1.y;
-								if (do_psi) {
+								if (psi_live) {
 									const float4 tq = (along >= 0.0f) ? pt[4 * p + 2] : pt[4 * p + 3];
 									const float q = tq.x * dx * dx + tq.y * dx * dy + tq.z * dy * dy;
 									psi_max = fmaxf(psi_max, __expf(-0.5f * q));
 								}
-								if (do_hd) {
+								if (hd_live) {
 									float v = 0.0f;
 									if (hd_ok && !(dist < 1e-9f)) {
 										const float crs = t1.x * dy - t1.y * dx;
@@ -767,10 +782,6 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 										v = g_dir * g_fov * hd_speed * fminf(1.0f, P.hd_dmin * inv);
 									}
 									hd_max = fmaxf(hd_max, v);
-								}
-								if (do_ps) {
-									const float clearance = fmaxf(dist - P.ps_min_dist, 0.0f);
-									ps_max = fmaxf(ps_max, sp_norm * __expf(-clearance));
 								}
 							}
 						} else {
