@@ -625,7 +625,8 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		if (want) {
 			tpc_threads = hmp_dev_tpc_max_threads();
 			// few candidates: smaller blocks so that every SM gets one
-			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes < ctx->sm_count) tpc_threads /= 2;
+			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes < ctx->sm_count)
+				tpc_threads = (tpc_threads > 128) ? 128 : 64;
 		}
 	}
 	size_t smem_sweep = smem;

@@ -112,6 +112,12 @@ __device__ __noinline__ PeopleMax people_critics_generic(const DevPerson* people
 	return m;
 }
 
+#ifndef HMP_TPC_DYN_UNROLL
+#define HMP_TPC_DYN_UNROLL 1
+#endif
+#ifndef HMP_TPC_PPL_UNROLL
+#define HMP_TPC_PPL_UNROLL 1
+#endif
 #ifndef HMP_TPC_LOCKSTEP
 #define HMP_TPC_LOCKSTEP 0
 #endif
@@ -125,13 +131,18 @@ __device__ __noinline__ PeopleMax people_critics_generic(const DevPerson* people
 #ifndef HMP_TPC_MIN_BLOCKS
 #define HMP_TPC_MIN_BLOCKS (512 / HMP_TPC_THREADS)
 #endif
+#ifdef HMP_TPC_MAXNREG
+__global__ void __maxnreg__(HMP_TPC_MAXNREG) sweep_tpc_kernel(const KernelArgs A) {
+#else
 __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc_kernel(const KernelArgs A) {
+#endif
 	using R = float;
 	using SC = float;
 	using TwistS = TwistT<float>;
 	constexpr int NW = HMP_TPC_THREADS / 32;
 	constexpr int TPC_UNROLL = HMP_TPC_UNROLL;   // static objects in flight per thread
-	[[maybe_unused]] constexpr int TPC_PAIR_UNROLL = HMP_TPC_PAIR_UNROLL;   // ... pairs of them in the packed loop
+	[[maybe_unused]] constexpr int TPC_PAIR_UNROLL = HMP_TPC_PAIR_UNROLL;
+	constexpr int TPC_DYN_UNROLL = HMP_TPC_DYN_UNROLL, TPC_PPL_UNROLL = HMP_TPC_PPL_UNROLL;   // dynamic objects / people in flight per thread   // ... pairs of them in the packed loop
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint64_t s_bar;
 	__shared__ double s_wbest[NW];
@@ -489,7 +500,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 					const int nd = (i == 0) ? S.n_dynamic : S.n_dynamic_later;
 					const R nine = (R)9 * Cst<R>::deg();
 					const R speed_r = speed_d;
-#pragma unroll 1
+#pragma unroll TPC_DYN_UNROLL
 					for (int k = 0; k < nd; ++k) {
 						const DevDynamic& o = dynamics[k];
 						R dx = (R)(fma(tnow, o.vx, o.d0x) - rxd), dy = (R)(fma(tnow, o.vy, o.d0y) - ryd);
@@ -744,7 +755,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc
 							const float mxu = tgx_d * inv_rs, myu = tgy_d * inv_rs;   // unit motion direction
 							const float hd_speed = rspeed * P.hd_inv_max_speed;
 							const float4* pt = reinterpret_cast<const float4*>(people);
-#pragma unroll 1
+#pragma unroll TPC_PPL_UNROLL
 							for (int p = 0; p < S.n_people; ++p) {
 								const float4 t0 = pt[4 * p], t1 = pt[4 * p + 1];   // warp-uniform addresses: broadcast
 								const float dx = rx - fmaf(tp, t0.z, t0.x), dy = ry - fmaf(tp, t0.w, t0.y);
