@@ -492,6 +492,15 @@ def _m_turning_people(p, sc):
         sc.world.people[i].vth = 0.4 if i % 2 else -0.25
 
 
+def _m_touching_obstacle(p, sc):
+    # an obstacle point that coincides with its robot-side point at t = 0 (zero-length distance vector: no force,
+    # social_force_model.cpp:461-480) and one a millimetre away: the degenerate-geometry guards of both sweep layouts
+    o = sc.world.obstacles[0]
+    o.obj_x, o.obj_y = o.robot_x, o.robot_y
+    o = sc.world.obstacles[1]
+    o.obj_x, o.obj_y = o.robot_x + 1e-3, o.robot_y
+
+
 def _m_empty_world(p, sc):
     sc.world.n_people = sc.world.n_groups = sc.world.n_obstacles = 0
 
@@ -507,7 +516,7 @@ def _m_near_edge(p, sc):
 
 VARIANTS = [_m_fis_off, _m_filter, _m_linear_fov, _m_maintain, _m_ttc_rollout, _m_sum_cross, _m_first_step_only,
             _m_stop_on_failure, _m_disable_interaction, _m_zero_scales, _m_no_people, _m_empty_world, _m_short_horizon,
-            _m_near_edge, _m_turning_people]
+            _m_near_edge, _m_turning_people, _m_touching_obstacle]
 
 
 @pytest.mark.parametrize("precise", [True, False], ids=["fp64", "fp32"])
