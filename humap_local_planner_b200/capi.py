@@ -143,7 +143,7 @@ ABI_SYMBOLS = (
     "hmp_get_explored_totals", "hmp_explain", "hmp_debug_world_to_map", "hmp_debug_footprint_cost",
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
     "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
-    "hmp_set_sweep_layout", "hmp_last_sweep_mode",
+    "hmp_set_sweep_layout", "hmp_last_sweep_mode", "hmp_last_num_leaders_round2",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -312,6 +312,11 @@ class Planner:
     def set_sweep_layout(self, layout: int = 0):
         """FP32 sweep: 0 automatic, 1 one warp per candidate, 2 one thread per candidate."""
         self._check(self._lib.hmp_set_sweep_layout(self._ctx, int(layout)))
+
+    def last_num_leaders_round2(self) -> int:
+        """Candidates re-scored by the second refinement round of the last single-scene plan in mode 2."""
+        self._lib.hmp_last_num_leaders_round2.argtypes = [C.c_void_p]
+        return int(self._lib.hmp_last_num_leaders_round2(self._ctx))
 
     def last_sweep_mode(self) -> int:
         """0 = the last main sweep ran one warp per candidate, else the block size of the thread-per-candidate kernel."""

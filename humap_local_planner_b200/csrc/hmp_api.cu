@@ -42,12 +42,13 @@ extern "C" cudaError_t hmp_dev_launch_env_closest(const HmpShape* shapes, const 
 extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, uint32_t stride, float radius, uint8_t* out,
                                              int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
-                                                      int32_t* leaders, int32_t* count, int n_scenes, cudaStream_t stream);
+                                                      int32_t* leaders, int32_t* count, const double* thr_lo, double* thr_out,
+                                                      int min_leaders, int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
                                                     const double* r_costs, const double* r_seeds, const double* r_poses,
                                                     const int32_t* r_nposes, double* totals_full, double* best_out, double* o_costs,
                                                     double* o_seeds, double* o_poses, double* o_total, int32_t* o_nposes,
-                                                    int n_scenes, cudaStream_t stream);
+                                                    int n_scenes, int merge, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
@@ -167,6 +168,9 @@ struct HmpContext {
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
 	int refine_max_leaders = 256;    // per scene (single-scene plans); batches use min(this, 32)
 	int last_n_leaders = 0;
+	int last_n_leaders2 = 0;        // ... of the second round (single-scene plans)
+	int refine_min_leaders = 16;     // the best-ranked candidates are refined whatever the window (HMP_REFINE_MIN_LEADERS)
+	int refine_rounds = 2;           // HMP_REFINE_ROUNDS=1 in the environment: first round only (A/B)
 	HmpEquisampled equi{};           // second generator of the pool (hmp_set_equisampled); enabled = 0 after hmp_create
 	std::vector<double> last_equi;   // its velocity samples of the last plan ([n][3])
 	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
@@ -709,6 +713,8 @@ HmpContext* hmp_create(int device_id) {
 	}
 	ctx->device = device_id;
 	ctx->prune_obstacle = getenv("HMP_NO_PRUNE") ? 0 : 1;
+	if (const char* e = getenv("HMP_REFINE_MIN_LEADERS")) ctx->refine_min_leaders = std::max(1, std::min(256, atoi(e)));
+	if (const char* e = getenv("HMP_REFINE_ROUNDS")) ctx->refine_rounds = std::max(1, std::min(2, atoi(e)));
 	if (const char* e = getenv("HMP_SWEEP_LAYOUT")) ctx->sweep_layout = std::max(0, std::min(2, atoi(e)));
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
@@ -1155,46 +1161,68 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const bool want_poses = (NS == 1);
 		const size_t nk = (size_t)NS * K;
 		const size_t r_doubles = nk * (HMP_NUM_COSTS + 3 + 1) + (want_poses ? nk * T * 3 : 0);
-		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + NS) * sizeof(int32_t);
-		if ((rc = ctx->d_refine.ensure(r_bytes))) return rc;
-		double* r_costs = (double*)ctx->d_refine.p;
-		double* r_seeds = r_costs + nk * HMP_NUM_COSTS;
-		double* r_totals = r_seeds + nk * 3;
-		double* r_poses = want_poses ? r_totals + nk : nullptr;
-		int32_t* r_leaders = (int32_t*)((double*)ctx->d_refine.p + r_doubles);
-		int32_t* r_nposes = r_leaders + nk;
-		int32_t* r_count = r_nposes + nk;
-		CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count, NS, st));
-		KernelArgs Rf = A;
-		Rf.precise = 1;
-		Rf.cand_list = r_leaders;
-		Rf.cand_list_stride = K;
-		Rf.n_work = K;
-		Rf.use_best_index = 0;
-		Rf.d_costs = r_costs;
-		Rf.d_seeds = r_seeds;
-		Rf.d_poses = r_poses;
-		Rf.totals = r_totals;
-		Rf.d_nposes = r_nposes;
-		Rf.d_forces = nullptr;
-		// single scene: few candidates, many SMs -> one candidate per BLOCK (block-cooperative instance), as many blocks as
-		// the GPU holds; batches have enough leaders in total to keep one warp per candidate
-		// The block-cooperative instance finishes a wave of <= sm_count leaders in ~0.85 ms (cfg2), the warp-per-candidate
-		// instance any number up to 2 x sm_count in ~1.4 ms; the count is only known on the device, so the choice follows
-		// the previous cycle's count (consecutive control cycles have similar leader sets).
-		if (NS == 1 && ctx->last_n_leaders <= ctx->sm_count) {
-			CU(hmp_dev_launch_plan(&Rf, std::min(K, ctx->sm_count), 3, smem, st));
-		} else if (NS == 1) {
-			Rf.warps_per_ticket = 2;
-			CU(hmp_dev_launch_plan(&Rf, (K + 1) / 2, 1, smem, st));
-		} else {
-			Rf.warps_per_ticket = HMP_WARPS_PER_BLOCK;
-			CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
+		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + NS) * sizeof(int32_t) + 8;   // one round's buffers, 8-byte aligned
+		const size_t r_set = (r_bytes + 15) / 16 * 16;
+		// single-scene plans run a second round (below): a second set of buffers + the first round's threshold
+		const int rounds = (NS == 1 && ctx->refine_rounds >= 2) ? 2 : 1;
+		if ((rc = ctx->d_refine.ensure(r_set * rounds + NS * sizeof(double)))) return rc;
+		double* r_thr = (double*)((unsigned char*)ctx->d_refine.p + r_set * rounds);
+		auto refine_round = [&](int round) -> int {
+			unsigned char* base = (unsigned char*)ctx->d_refine.p + r_set * round;
+			double* r_costs = (double*)base;
+			double* r_seeds = r_costs + nk * HMP_NUM_COSTS;
+			double* r_totals = r_seeds + nk * 3;
+			double* r_poses = want_poses ? r_totals + nk : nullptr;
+			int32_t* r_leaders = (int32_t*)((double*)base + r_doubles);
+			int32_t* r_nposes = r_leaders + nk;
+			int32_t* r_count = r_nposes + nk;
+			CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
+			                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, st));
+			KernelArgs Rf = A;
+			Rf.precise = 1;
+			Rf.cand_list = r_leaders;
+			Rf.cand_list_stride = K;
+			Rf.n_work = K;
+			Rf.use_best_index = 0;
+			Rf.d_costs = r_costs;
+			Rf.d_seeds = r_seeds;
+			Rf.d_poses = r_poses;
+			Rf.totals = r_totals;
+			Rf.d_nposes = r_nposes;
+			Rf.d_forces = nullptr;
+			// single scene: few candidates, many SMs -> one candidate per BLOCK (block-cooperative instance), as many blocks as
+			// the GPU holds; batches have enough leaders in total to keep one warp per candidate
+			// The block-cooperative instance finishes a wave of <= sm_count leaders in ~0.85 ms (cfg2), the warp-per-candidate
+			// instance any number up to 2 x sm_count in ~1.4 ms; the count is only known on the device, so the choice follows
+			// the previous cycle's count (consecutive control cycles have similar leader sets). The second round's list is
+			// almost always empty (its blocks find no candidate and leave): one warp per candidate, two per block.
+			if (NS == 1 && round == 0 && ctx->last_n_leaders <= ctx->sm_count) {
+				CU(hmp_dev_launch_plan(&Rf, std::min(K, ctx->sm_count), 3, smem, st));
+			} else if (NS == 1) {
+				Rf.warps_per_ticket = 2;
+				CU(hmp_dev_launch_plan(&Rf, (K + 1) / 2, 1, smem, st));
+			} else {
+				Rf.warps_per_ticket = HMP_WARPS_PER_BLOCK;
+				CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
+			}
+			CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
+			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, st));
+			ctx->launches += 3;
+			if (round == 0) CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+			else CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+			return HMP_OK;
+		};
+		// Round 1: leaders within the window of the FP32 best. Round 2: the window above the REFINED best of round 1, minus
+		// what round 1 covered -- empty unless the FP32 best was a candidate whose FP32 total is far too low (a chaotic
+		// rollout): then the candidates between the two thresholds could beat its FP64 total and are refined too. After
+		// round 2 every candidate whose FP32 total lies within the window of the final (FP64) best has been refined.
+		// The work ticket is reset between the rounds (both rollouts pull candidates from it).
+		ctx->last_n_leaders2 = 0;
+		if ((rc = refine_round(0))) return rc;
+		if (rounds == 2) {
+			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
+			if ((rc = refine_round(1))) return rc;
 		}
-		CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
-		                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, st));
-		ctx->launches += 3;
-		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
 	CU(cudaEventRecord(ctx->ev1, st));
 	CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
@@ -1961,6 +1989,8 @@ int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders) 
 }
 
 int hmp_last_num_leaders(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders : -1; }
+
+int hmp_last_num_leaders_round2(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders2 : -1; }
 
 int64_t hmp_launch_count(HmpContext* ctx) { return ctx ? ctx->launches : 0; }
 

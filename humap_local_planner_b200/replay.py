@@ -141,7 +141,7 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
             log.best.append(res.best_index)
             if res.status == 0:
                 cmd_x, cmd_th = res.xv, res.thetav
-            if on_plan is not None and on_plan_every and (len(log.plan_ms) % on_plan_every == 1):
+            if on_plan is not None and on_plan_every and (on_plan_every == 1 or len(log.plan_ms) % on_plan_every == 1):
                 if grids is None:
                     grids = [planner.get_mapgrid(g, base.cells.shape) for g in range(4)]
                 from .capi import Scene

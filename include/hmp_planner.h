@@ -325,6 +325,11 @@ int hmp_set_precision(HmpContext* ctx, int32_t fp64);
 int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders);
 /* Leaders re-scored in FP64 by the last plan of scene 0 (0 in modes 0 / 1), -1 if there is no plan. */
 int hmp_last_num_leaders(HmpContext* ctx);
+/* Single-scene plans in mode 2 run a second refinement round: the window is taken once more above the REFINED best of the
+ * first round and the candidates between the two thresholds are refined as well, so that every candidate whose FP32 total
+ * lies within the window of the final (FP64) best has been re-scored even when the FP32 best was a rollout with a large
+ * FP32 error. Returns how many candidates that second round re-scored in the last plan (almost always 0). */
+int hmp_last_num_leaders_round2(HmpContext* ctx);
 /* Work layout of the FP32 sweep (modes 0 and 2): 0 (default) = automatic, 1 = one warp per candidate (lanes stride over the
  * objects; shortest latency for a few thousand candidates), 2 = one thread per candidate (a warp rolls out 32 candidates,
  * the per-step scalar section is issued once per 32; highest throughput from ~16k candidates per launch). Both layouts
