@@ -33,6 +33,7 @@ class ReplayLog:
     best: List[int] = field(default_factory=list)
     poses: List[tuple] = field(default_factory=list)
     goals_reached: int = 0
+    recoveries: int = 0                                       # cycles without a valid trajectory (the host backs off)
     parity_checked: int = 0
     parity_mismatch: int = 0
 
@@ -141,6 +142,12 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
             log.best.append(res.best_index)
             if res.status == 0:
                 cmd_x, cmd_th = res.xv, res.thetav
+            else:
+                # no valid trajectory: what RecoveryManager does on the host in the reference (src/recovery_manager.cpp) is out
+                # of scope here; the harness backs off along the heading at min_vel_x and turns slowly until a plan exists again
+                log.recoveries += 1
+                cmd_x = max(min(L.min_vel_x, 0.0), vx - L.acc_lim_x * period) if L.min_vel_x < 0 else 0.0
+                cmd_th = min(L.min_vel_theta, vth + L.acc_lim_theta * period)
             if on_plan is not None and on_plan_every and (on_plan_every == 1 or len(log.plan_ms) % on_plan_every == 1):
                 if grids is None:
                     grids = [planner.get_mapgrid(g, base.cells.shape) for g in range(4)]
@@ -179,7 +186,8 @@ def summarize(log: ReplayLog) -> dict:
     return {"cycles": len(log.states), "move_cycles": len(log.plan_ms), "goals_reached": log.goals_reached,
             "p50_cycle_ms": float(np.percentile(ms, 50)), "p99_cycle_ms": float(np.percentile(ms, 99)),
             "p50_gpu_ms": float(np.percentile(g, 50)), "p99_gpu_ms": float(np.percentile(g, 99)),
-            "state_sequence_head": seq[:12], "parity_checked": log.parity_checked, "parity_mismatch": log.parity_mismatch}
+            "state_sequence_head": seq[:12], "parity_checked": log.parity_checked, "parity_mismatch": log.parity_mismatch,
+            "recoveries": log.recoveries}
 
 
 if __name__ == "__main__":
