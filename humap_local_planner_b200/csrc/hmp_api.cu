@@ -17,6 +17,7 @@
 #include <limits>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "hmp_device.h"
@@ -176,6 +177,8 @@ struct HmpContext {
 	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
 	int dilated_scenes = 0;
 	int prune_obstacle = 1;          // HMP_NO_PRUNE=1 in the environment disables the dilated-map pruning (A/B timing)
+	HostBuf h_grid_stage[2];         // pinned staging of hmp_plan_batch's MapGrids (float), double-buffered
+	cudaEvent_t grid_stage_ev[2] = {nullptr, nullptr};
 	int sweep_layout = 0;            // FP32 sweep: 0 auto, 1 one warp per candidate, 2 one thread per candidate (hmp_set_sweep_layout)
 	int last_sweep_mode = 0;         // launch mode of the last main sweep (0 warp per candidate, else threads per block of the thread-per-candidate kernel)
 
@@ -759,6 +762,10 @@ void hmp_destroy(HmpContext* ctx) {
 	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
+	for (int b = 0; b < 2; ++b) {
+		ctx->h_grid_stage[b].release();
+		if (ctx->grid_stage_ev[b]) cudaEventDestroy(ctx->grid_stage_ev[b]);
+	}
 	ctx->h_out.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1407,19 +1414,43 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		return HMP_E_INVALID;
 	}
 	if (any_grid) {
-		float* f = (float*)hs;
-		for (int s = 0; s < n_scenes; ++s) {
-			for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
-				if (!target_dist[g]) {
-					set_err("target_dist[%d] is null", g);
-					return HMP_E_INVALID;
-				}
-				const double* src = target_dist[g] + (size_t)s * n;
-				for (size_t i = 0; i < n; ++i) f[i] = (float)src[i];
-				CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + ((size_t)s * HMP_NUM_MAPGRIDS + g) * n, f, n * sizeof(float),
-				                   cudaMemcpyHostToDevice, ctx->stream));
-				CU(cudaStreamSynchronize(ctx->stream));
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+			if (!target_dist[g]) {
+				set_err("target_dist[%d] is null", g);
+				return HMP_E_INVALID;
 			}
+		}
+		// double -> float conversion of n_scenes x 4 grids (328 MB for 512 scenes of 200 x 200) by all host threads into two
+		// pinned staging buffers; the copy of one chunk of scenes overlaps the conversion of the next
+		const size_t scene_floats = n * HMP_NUM_MAPGRIDS;
+		const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_scenes, ((size_t)48 << 20) / (scene_floats * sizeof(float))));
+		if ((rc = ctx->h_grid_stage[0].ensure((size_t)chunk * scene_floats * sizeof(float)))) return rc;
+		if ((rc = ctx->h_grid_stage[1].ensure((size_t)chunk * scene_floats * sizeof(float)))) return rc;
+		for (int b = 0; b < 2; ++b)
+			if (!ctx->grid_stage_ev[b]) CU(cudaEventCreateWithFlags(&ctx->grid_stage_ev[b], cudaEventDisableTiming));
+		const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		int buf = 0;
+		for (int s0 = 0; s0 < n_scenes; s0 += chunk, buf ^= 1) {
+			const int ns = std::min(chunk, n_scenes - s0);
+			if (s0 >= 2 * chunk) CU(cudaEventSynchronize(ctx->grid_stage_ev[buf]));   // the copy that last read this buffer
+			float* f = (float*)ctx->h_grid_stage[buf].p;
+			const size_t items = (size_t)ns * HMP_NUM_MAPGRIDS;   // (scene, grid) pairs of this chunk
+			const unsigned nt = (unsigned)std::min<size_t>(hw, items);
+			auto work = [&](unsigned t) {
+				for (size_t it = t; it < items; it += nt) {
+					const int s = s0 + (int)(it / HMP_NUM_MAPGRIDS), g = (int)(it % HMP_NUM_MAPGRIDS);
+					const double* src = target_dist[g] + (size_t)s * n;
+					float* dst = f + it * n;
+					for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+				}
+			};
+			std::vector<std::thread> pool;
+			for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+			work(0);
+			for (auto& th : pool) th.join();
+			CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + (size_t)s0 * scene_floats, f, items * n * sizeof(float), cudaMemcpyHostToDevice,
+			                   ctx->stream));
+			CU(cudaEventRecord(ctx->grid_stage_ev[buf], ctx->stream));
 		}
 		for (bool& b : ctx->have_grid) b = true;
 	}
