@@ -1047,6 +1047,8 @@ def test_error_codes():
         w.n_people = -1
         assert code(pl.plan, w, smp) == capi.HMP_E_INVALID
         assert code(pl.set_refinement, -0.1, 16) == capi.HMP_E_INVALID
+        assert code(pl.set_sweep_layout, 3) == capi.HMP_E_INVALID and code(pl.set_sweep_layout, -1) == capi.HMP_E_INVALID
+        assert pl.last_num_leaders_round2() == -1   # no plan yet
         assert code(pl.explored_totals, 5) in (capi.HMP_E_NOT_READY, capi.HMP_E_INVALID)
         env = scenes.make_env_params(robot_model=2)                                    # two-circle model: not built
         shapes, verts = scenes.make_shapes(0, 4)
