@@ -306,7 +306,7 @@ class Planner:
         """False / 0: FP32 object loops; True / 1: FP64 (parity mode); 2: FP32 sweep + FP64 refinement of the leaders."""
         self._check(self._lib.hmp_set_precision(self._ctx, int(mode)))
 
-    def set_refinement(self, rel_window: float = 0.02, max_leaders: int = 256):
+    def set_refinement(self, rel_window: float = 0.02, max_leaders: int = 0):
         self._check(self._lib.hmp_set_refinement(self._ctx, float(rel_window), int(max_leaders)))
 
     def set_sweep_layout(self, layout: int = 0):

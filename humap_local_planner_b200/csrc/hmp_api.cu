@@ -167,7 +167,8 @@ struct HmpContext {
 	bool have_footprint = false;
 	int precise = 2;                 // 0 FP32, 1 FP64, 2 (default) FP32 sweep + FP64 refinement of the leaders
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
-	int refine_max_leaders = 256;    // per scene (single-scene plans); batches use min(this, 32)
+	int refine_max_leaders = 0;      // per scene; 0 (default) = the SM count (single-scene plans: one block-cooperative FP64 rollout
+	                                 // per SM, a single wave); batches use min(this or 256, 32)
 	int last_n_leaders = 0;
 	int last_n_leaders2 = 0;        // ... of the second round (single-scene plans)
 	int refine_min_leaders = 16;     // the best-ranked candidates are refined whatever the window (HMP_REFINE_MIN_LEADERS)
@@ -1164,7 +1165,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		ctx->last_n_leaders = 0;
 	} else {
 		// selection refinement: leaders of the FP32 sweep -> FP64 rollouts -> winner among the refined totals
-		const int K = (NS == 1) ? ctx->refine_max_leaders : std::min(ctx->refine_max_leaders, 32);
+		const int K = (NS == 1) ? (ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : ctx->sm_count)
+		                        : std::min(ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : 256, 32);
 		const bool want_poses = (NS == 1);
 		const size_t nk = (size_t)NS * K;
 		const size_t r_doubles = nk * (HMP_NUM_COSTS + 3 + 1) + (want_poses ? nk * T * 3 : 0);
@@ -1172,7 +1174,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const size_t r_set = (r_bytes + 15) / 16 * 16;
 		// single-scene plans run a second round (below): a second set of buffers + the first round's threshold
 		const int rounds = (NS == 1 && ctx->refine_rounds >= 2) ? 2 : 1;
-		if ((rc = ctx->d_refine.ensure(r_set * rounds + NS * sizeof(double)))) return rc;
+		if ((rc = ctx->d_refine.ensure(r_set * rounds + 2 * NS * sizeof(double)))) return rc;   // + (threshold, effective window) of round 1
 		double* r_thr = (double*)((unsigned char*)ctx->d_refine.p + r_set * rounds);
 		auto refine_round = [&](int round) -> int {
 			unsigned char* base = (unsigned char*)ctx->d_refine.p + r_set * round;
@@ -2010,12 +2012,12 @@ int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq) {
 }
 
 int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders) {
-	if (!ctx || !(rel_window >= 0.0) || max_leaders < 1 || max_leaders > 4096) {
-		set_err("bad refinement arguments (window >= 0, 1 <= max_leaders <= 4096)");
+	if (!ctx || !(rel_window >= 0.0) || max_leaders < 0 || max_leaders > 4096) {
+		set_err("bad refinement arguments (window >= 0, 0 <= max_leaders <= 4096; 0 = the SM count)");
 		return HMP_E_INVALID;
 	}
 	ctx->refine_window = rel_window;
-	ctx->refine_max_leaders = (max_leaders + 7) / 8 * 8;
+	ctx->refine_max_leaders = (max_leaders + 7) / 8 * 8;   // 0 stays 0: automatic
 	return HMP_OK;
 }
 

@@ -319,9 +319,10 @@ int hmp_set_params(HmpContext* ctx, const HmpParams* params);
  * in HmpResult are then those of the FP64 path at a few percent of extra time.
  * Pose integration, twist / limit arithmetic, cell indexing and the weighted total are FP64 in every mode. */
 int hmp_set_precision(HmpContext* ctx, int32_t fp64);
-/* Mode 2 only: relative window above the best FP32 total (default 0.02) and the cap on leaders per scene (default 256,
- * rounded up to a multiple of 8; batches use at most 32). If more candidates fall inside the window it is halved until
- * they fit. No reference counterpart. */
+/* Mode 2 only: relative window above the best FP32 total (default 0.02) and the cap on leaders per scene (rounded up to a
+ * multiple of 8; batches use at most 32). Until this is called (and for max_leaders = 0) the cap is the SM count of the device, so that the leaders
+ * of a single-scene plan are one wave of block-cooperative FP64 rollouts. If more candidates fall inside the window it
+ * shrinks to the widest window that holds at most the cap; fewer than 16 widens it. No reference counterpart. */
 int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders);
 /* Leaders re-scored in FP64 by the last plan of scene 0 (0 in modes 0 / 1), -1 if there is no plan. */
 int hmp_last_num_leaders(HmpContext* ctx);

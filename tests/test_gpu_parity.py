@@ -762,6 +762,7 @@ def test_refinement_window_and_cap(planner):
     planner.set_refinement(0.02, 256)
     res, _ = planner.plan(sc.world, smp)
     n = planner.last_num_leaders()
+    planner.set_refinement(0.02, 0)     # back to the default cap (the SM count)
     planner.set_precision(False)
     assert 1 <= n_small <= 16 and n_small <= n <= 256
     assert res_small.best_index == res.best_index and res_small.best_total == res.best_total
