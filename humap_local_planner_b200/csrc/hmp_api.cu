@@ -1176,6 +1176,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const int rounds = (NS == 1 && ctx->refine_rounds >= 2) ? 2 : 1;
 		if ((rc = ctx->d_refine.ensure(r_set * rounds + 2 * NS * sizeof(double)))) return rc;   // + (threshold, effective window) of round 1
 		double* r_thr = (double*)((unsigned char*)ctx->d_refine.p + r_set * rounds);
+		int32_t* r_count_dev[2] = {nullptr, nullptr};
 		auto refine_round = [&](int round) -> int {
 			unsigned char* base = (unsigned char*)ctx->d_refine.p + r_set * round;
 			double* r_costs = (double*)base;
@@ -1217,8 +1218,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
 			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, st));
 			ctx->launches += 3;
-			if (round == 0) CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-			else CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+			r_count_dev[round] = r_count;   // read back after the last round (a copy to pageable memory here would stall the
+			                                // host, and with it the launches of the next round, until this round has finished)
 			return HMP_OK;
 		};
 		// Round 1: leaders within the window of the FP32 best. Round 2: the window above the REFINED best of round 1, minus
@@ -1232,6 +1233,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 			if ((rc = refine_round(1))) return rc;
 		}
+		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		if (r_count_dev[1]) CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
 	CU(cudaEventRecord(ctx->ev1, st));
 	CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
