@@ -30,7 +30,7 @@ static_assert(sizeof(DevDynamic) == 64 && sizeof(DevPerson) == 64 && sizeof(DevG
 extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_stride, int costmap_in_smem);
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
-extern "C" cudaError_t hmp_dev_occupancy_tpc(size_t smem, int threads, int* blocks_per_sm);
+extern "C" cudaError_t hmp_dev_occupancy_tpc(size_t smem, int threads, int rich, int* blocks_per_sm);
 extern "C" int hmp_dev_tpc_max_threads();
 extern "C" size_t hmp_dev_tpc_extra_smem(uint32_t scene_stride);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
@@ -645,8 +645,14 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 			smem_sweep = smem;
 		}
 	}
+	// few warps per SM sub-partition anyway (<= 2): the register-rich instance of the thread-per-candidate sweep
+	int tpc_rich = 0;
+	if (tpc_threads) {
+		const long long warps = (((long long)C + tpc_threads - 1) / tpc_threads) * pl.n_scenes * (tpc_threads / 32);
+		tpc_rich = (warps <= (long long)ctx->sm_count * 8 && !getenv("HMP_TPC_NO_RICH")) ? 1 : 0;
+	}
 	int bps = 0;
-	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, &bps));
+	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, tpc_rich, &bps));
 	else CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
@@ -670,7 +676,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		}
 	}
 	if (getenv("HMP_DEBUG")) fprintf(stderr, "[hmp] smem %zu B/block, %d blocks/SM resident, %lld blocks per scene, %d scenes, sweep mode %d\n", smem, bps, per_scene, pl.n_scenes, tpc_threads);
-	if (sweep_mode_out) *sweep_mode_out = tpc_threads;
+	if (sweep_mode_out) *sweep_mode_out = tpc_threads ? (tpc_threads | (tpc_rich ? 1024 : 0)) : 0;
 	if (smem_sweep_out) *smem_sweep_out = smem_sweep;
 	*blocks_x_out = (int)per_scene;
 	*smem_out = smem;
@@ -1996,7 +2002,7 @@ int hmp_set_sweep_layout(HmpContext* ctx, int32_t layout) {
 	return HMP_OK;
 }
 
-int hmp_last_sweep_mode(HmpContext* ctx) { return ctx ? ctx->last_sweep_mode : -1; }
+int hmp_last_sweep_mode(HmpContext* ctx) { return ctx ? (ctx->last_sweep_mode & 1023) : -1; }   // bit 10 = register-rich instance
 
 int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq) {
 	if (!ctx) {

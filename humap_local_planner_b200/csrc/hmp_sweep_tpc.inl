@@ -131,10 +131,15 @@ __device__ __noinline__ PeopleMax people_critics_generic(const DevPerson* people
 #ifndef HMP_TPC_MIN_BLOCKS
 #define HMP_TPC_MIN_BLOCKS (512 / HMP_TPC_THREADS)
 #endif
+// MINB = resident blocks per SM the registers are budgeted for: 2 (128 registers, 16 warps per SM) for launches that fill the
+// GPU, 1 (up to 255 registers: the kernel takes ~200 and loses its spills) for launches that leave at most two warps per SM
+// sub-partition anyway -- there a warp's speed is pure latency and the extra registers are free (cfg1: sweep 1.59 -> 1.52 ms).
 #ifdef HMP_TPC_MAXNREG
+template <int MINB>
 __global__ void __maxnreg__(HMP_TPC_MAXNREG) sweep_tpc_kernel(const KernelArgs A) {
 #else
-__global__ void __launch_bounds__(HMP_TPC_THREADS, HMP_TPC_MIN_BLOCKS) sweep_tpc_kernel(const KernelArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const KernelArgs A) {
 #endif
 	using R = float;
 	using SC = float;
