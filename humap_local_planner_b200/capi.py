@@ -144,6 +144,7 @@ ABI_SYMBOLS = (
     "hmp_debug_fis", "hmp_debug_last_forces", "hmp_num_steps", "hmp_launch_count", "hmp_set_precision", "hmp_compute_mapgrid", "hmp_get_mapgrid",
     "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
     "hmp_set_sweep_layout", "hmp_last_sweep_mode", "hmp_last_num_leaders_round2",
+    "hmp_compute_mapgrid_batch", "hmp_set_mapgrids_batch_f32", "hmp_last_num_scenes", "hmp_last_fallback_rounds",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -179,7 +180,14 @@ def load_library() -> C.CDLL:
     lib.hmp_plan.argtypes = [C.c_void_p, P(HmpWorld), P(HmpSampling), C.c_void_p, _i, P(HmpResult), C.c_void_p, _i]
     lib.hmp_plan_batch.argtypes = [C.c_void_p, P(HmpWorld), _i, C.c_void_p, C.c_void_p, C.c_void_p, P(HmpSampling),
                                    P(HmpResult)]
-    lib.hmp_replan_resident.argtypes = [C.c_void_p, P(HmpResult)]
+    lib.hmp_replan_resident.argtypes = [C.c_void_p, P(HmpResult), _i]
+    lib.hmp_compute_mapgrid_batch.argtypes = [C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hmp_compute_mapgrid_batch.restype = C.c_int
+    lib.hmp_set_mapgrids_batch_f32.argtypes = [C.c_void_p, _i, C.c_void_p]
+    lib.hmp_set_mapgrids_batch_f32.restype = C.c_int
+    for name in ("hmp_last_num_scenes", "hmp_last_fallback_rounds", "hmp_last_num_leaders_round2"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = C.c_int
     lib.hmp_get_explored_totals.argtypes = [C.c_void_p, C.c_void_p, _i]
     lib.hmp_explain.argtypes = [C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hmp_debug_world_to_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _i, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -315,8 +323,14 @@ class Planner:
 
     def last_num_leaders_round2(self) -> int:
         """Candidates re-scored by the second refinement round of the last single-scene plan in mode 2."""
-        self._lib.hmp_last_num_leaders_round2.argtypes = [C.c_void_p]
         return int(self._lib.hmp_last_num_leaders_round2(self._ctx))
+
+    def last_fallback_rounds(self) -> int:
+        """Extra refinement rounds the last plan needed because FP64 rejected every leader (mode 2)."""
+        return int(self._lib.hmp_last_fallback_rounds(self._ctx))
+
+    def last_num_scenes(self) -> int:
+        return int(self._lib.hmp_last_num_scenes(self._ctx))
 
     def last_sweep_mode(self) -> int:
         """0 = the last main sweep ran one warp per candidate, else the block size of the thread-per-candidate kernel."""
@@ -402,22 +416,51 @@ class Planner:
                                        _ptr(poses), MAX_STEPS if want_poses else 0))
         return res, (poses[: max(res.n_poses, 0)] if want_poses else None)
 
-    def plan_batch(self, worlds: Sequence[HmpWorld], cells: np.ndarray, grids: Sequence[np.ndarray],
+    def plan_batch(self, worlds, cells: Optional[np.ndarray], grids: Optional[Sequence[np.ndarray]],
                    sampling: HmpSampling, hv_prev: Optional[np.ndarray] = None):
-        """cells: [n][size_y][size_x] uint8; grids: 4 arrays [n][size_y][size_x] float64."""
+        """worlds: sequence of HmpWorld or a ctypes HmpWorld array; cells: [n][size_y][size_x] uint8 or None (costmaps of an
+        earlier batch call stay); grids: 4 arrays [n][size_y][size_x] float64, or None (grids left resident by
+        compute_mapgrid_batch / set_mapgrids_batch_f32 / an earlier batch)."""
         n = len(worlds)
-        arr = (HmpWorld * n)(*worlds)
-        cells = np.ascontiguousarray(cells, dtype=np.uint8)
-        gs = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
-        gp = (C.c_void_p * NUM_MAPGRIDS)(*[g.ctypes.data for g in gs])
+        arr = worlds if isinstance(worlds, C.Array) else (HmpWorld * n)(*worlds)
+        cells = None if cells is None else np.ascontiguousarray(cells, dtype=np.uint8)
+        gp = None
+        if grids is not None:
+            gs = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
+            gp = (C.c_void_p * NUM_MAPGRIDS)(*[g.ctypes.data for g in gs])
         hv = None if hv_prev is None else np.ascontiguousarray(hv_prev, dtype=np.float64)
         res = (HmpResult * n)()
         self._check(self._lib.hmp_plan_batch(self._ctx, arr, n, _ptr(cells), gp, _ptr(hv), C.byref(sampling), res))
         return list(res)
 
-    def replan_resident(self, n_scenes: int = 1):
-        res = (HmpResult * n_scenes)()
-        self._check(self._lib.hmp_replan_resident(self._ctx, res))
+    def compute_mapgrid_batch(self, cells: Optional[np.ndarray], plans, local_goal: Sequence[bool], n_scenes: Optional[int] = None):
+        """Wave fronts of n_scenes x 4 grids on the device. plans[g] = (plan_xy [total poses][2], plan_start [n_scenes + 1])."""
+        if cells is not None:
+            cells = np.ascontiguousarray(cells, dtype=np.uint8)
+            n_scenes = cells.shape[0]
+        xy = [np.ascontiguousarray(p[0], dtype=np.float64).reshape(-1, 2) for p in plans]
+        st = [np.ascontiguousarray(p[1], dtype=np.int32) for p in plans]
+        assert all(s.shape[0] == n_scenes + 1 for s in st)
+        xp = (C.c_void_p * NUM_MAPGRIDS)(*[a.ctypes.data for a in xy])
+        sp = (C.c_void_p * NUM_MAPGRIDS)(*[a.ctypes.data for a in st])
+        lg = np.ascontiguousarray([1 if b else 0 for b in local_goal], dtype=np.int32)
+        self._check(self._lib.hmp_compute_mapgrid_batch(self._ctx, int(n_scenes), _ptr(cells), xp, sp, _ptr(lg)))
+
+    def set_mapgrids_batch_f32(self, grids: Sequence[np.ndarray]):
+        """grids: 4 float32 arrays [n][size_y][size_x] (ideally in pinned memory), uploaded without conversion."""
+        gs = [np.ascontiguousarray(g, dtype=np.float32) for g in grids]
+        gp = (C.c_void_p * NUM_MAPGRIDS)(*[g.ctypes.data for g in gs])
+        self._check(self._lib.hmp_set_mapgrids_batch_f32(self._ctx, int(gs[0].shape[0]), gp))
+
+    def replan_resident(self, n_scenes: Optional[int] = None):
+        """Re-runs the last plan on the resident scene data; returns one HmpResult per scene of that plan."""
+        n_last = self.last_num_scenes()
+        if n_last < 0:
+            raise HmpError(HMP_E_NOT_READY, "no previous plan to re-run")
+        if n_scenes is not None and n_scenes != n_last:
+            raise HmpError(HMP_E_INVALID, f"the last plan had {n_last} scene(s), not {n_scenes}")
+        res = (HmpResult * n_last)()
+        self._check(self._lib.hmp_replan_resident(self._ctx, res, n_last))
         return list(res)
 
     # ---- diagnostics ---------------------------------------------------------------------------

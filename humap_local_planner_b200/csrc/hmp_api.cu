@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <new>
 #include <numeric>
@@ -44,12 +45,14 @@ extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, 
                                              int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
                                                       int32_t* leaders, int32_t* count, const double* thr_lo, double* thr_out,
-                                                      int min_leaders, int n_scenes, cudaStream_t stream);
+                                                      int min_leaders, int n_scenes, const int32_t* active, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_reselect(const double* totals, int C, double* best_out, const int32_t* active, int n_scenes,
+                                               cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
                                                     const double* r_costs, const double* r_seeds, const double* r_poses,
                                                     const int32_t* r_nposes, double* totals_full, double* best_out, double* o_costs,
                                                     double* o_seeds, double* o_poses, double* o_total, int32_t* o_nposes,
-                                                    int n_scenes, int merge, cudaStream_t stream);
+                                                    int n_scenes, int merge, const int32_t* active, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
@@ -58,6 +61,9 @@ extern "C" cudaError_t hmp_dev_launch_wavefront(const uint8_t* cm, int sx, int s
                                                 cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_wavefront_queue(const uint8_t* cm, int sx, int sy, const int* seeds, int n_seeds, float* dist,
                                                       int* status, cudaStream_t stream);
+extern "C" size_t hmp_dev_wavefront_smem(int sx, int sy, int queue);
+extern "C" cudaError_t hmp_dev_launch_wavefront_batch(const uint8_t* cms, uint32_t cm_stride, int sx, int sy, const int* seeds,
+                                                      const int* seed_off, float* dist, int* status, int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_fis(const double* in4, int n, double* out2, int precise, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_ffma_peak(int blocks, int iters, float* sink, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_cost_cloud(const DevParams* P, int n_cells, const uint8_t* cm, const float* mapgrids, const double* hv,
@@ -163,7 +169,9 @@ struct HmpContext {
 	bool have_grid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	double hv_prev[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	std::vector<double> footprint;
-	std::vector<uint8_t> h_cells;   // host copy of the single-scene costmap (seed test of the device wave front)
+	std::vector<uint8_t> h_cells;   // host copy of the single-scene costmap (scene 0 after a batch): seed test of the device wave front
+	int costmap_scenes = 0;         // scenes whose costmap is resident in d_costmaps (1 after hmp_set_costmap, n after a batch upload)
+	int batch_grid_scenes = 0;      // scenes whose four MapGrids are resident in d_mapgrids from a batch call (0: single-scene slots only)
 	bool have_footprint = false;
 	int precise = 2;                 // 0 FP32, 1 FP64, 2 (default) FP32 sweep + FP64 refinement of the leaders
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
@@ -171,6 +179,8 @@ struct HmpContext {
 	                                 // per SM, a single wave); batches use min(this or 256, 32)
 	int last_n_leaders = 0;
 	int last_n_leaders2 = 0;        // ... of the second round (single-scene plans)
+	int last_explain_n = 0, last_explain_T = 0;   // shape of the forces hmp_explain left in h_out (0: overwritten since)
+	int last_fallback_rounds = 0;   // extra refinement rounds of the last plan because FP64 rejected every leader (mode 2)
 	int refine_min_leaders = 16;     // the best-ranked candidates are refined whatever the window (HMP_REFINE_MIN_LEADERS)
 	int refine_rounds = 2;           // HMP_REFINE_ROUNDS=1 in the environment: first round only (A/B)
 	HmpEquisampled equi{};           // second generator of the pool (hmp_set_equisampled); enabled = 0 after hmp_create
@@ -191,7 +201,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask;
 	HostBuf h_stage, h_out;
 	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
@@ -633,7 +643,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		if (want) {
 			tpc_threads = hmp_dev_tpc_max_threads();
 			// few candidates: smaller blocks so that every SM gets one
-			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes < ctx->sm_count)
+			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes * 10 < (long long)ctx->sm_count * 9)
 				tpc_threads = (tpc_threads > 128) ? 128 : 64;
 		}
 	}
@@ -766,7 +776,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->wf_done[g]) cudaEventDestroy(ctx->wf_done[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	for (int b = 0; b < 2; ++b) {
@@ -836,6 +846,8 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
 	ctx->origin_y = origin_y;
 	ctx->resolution = resolution;
 	ctx->have_costmap = true;
+	ctx->costmap_scenes = 1;
+	ctx->batch_grid_scenes = 0;
 	ctx->last_valid = false;
 	ctx->dilated_dirty = true;
 	return HMP_OK;
@@ -882,6 +894,7 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 	}
 	CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + (size_t)grid * n, f, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 	ctx->have_grid[grid] = true;
+	ctx->batch_grid_scenes = 0;
 	ctx->hv_prev[grid] = highest_valid_cost_prev;
 	ctx->last_valid = false;
 	return HMP_OK;
@@ -917,7 +930,56 @@ static int resolve_wavefronts(HmpContext* ctx) {
 }
 
 // Host part of base_local_planner::MapGrid::setTargetCells / setLocalGoal [RECALLED, SURVEY App. B]: densify the plan
-// to the costmap resolution (adjustPlanResolution) and collect the seed cells; the wave front itself runs on the device.
+// to the costmap resolution (adjustPlanResolution) and collect the seed cells of the wave front (every on-map,
+// known plan cell up to the first gap; the local-goal variant seeds only the last one of them).
+static void collect_seeds(const HmpContext* ctx, const uint8_t* cells, const double* plan_xy, int n_plan, int local_goal,
+                          std::vector<int>& seeds) {
+	seeds.clear();
+	if (n_plan <= 0) return;
+	const int sx = ctx->size_x, sy = ctx->size_y;
+	auto world_to_map = [&](double wx, double wy, int& mx, int& my) {
+		if (wx < ctx->origin_x || wy < ctx->origin_y) return false;
+		mx = (int)((wx - ctx->origin_x) / ctx->resolution);
+		my = (int)((wy - ctx->origin_y) / ctx->resolution);
+		return mx < sx && my < sy;
+	};
+	std::vector<double> px, py;
+	double last_x = plan_xy[0], last_y = plan_xy[1];
+	px.push_back(last_x);
+	py.push_back(last_y);
+	const double min_sq = ctx->resolution * ctx->resolution;
+	for (int i = 1; i < n_plan; ++i) {
+		double lx = plan_xy[2 * i], ly = plan_xy[2 * i + 1];
+		double sq = (lx - last_x) * (lx - last_x) + (ly - last_y) * (ly - last_y);
+		if (sq > min_sq) {
+			int steps = (int)std::ceil(std::sqrt(sq) / ctx->resolution);
+			double dx = (lx - last_x) / steps, dy = (ly - last_y) / steps;
+			for (int j = 1; j < steps; ++j) {
+				px.push_back(last_x + j * dx);
+				py.push_back(last_y + j * dy);
+			}
+		}
+		px.push_back(lx);
+		py.push_back(ly);
+		last_x = lx;
+		last_y = ly;
+	}
+	bool started = false;
+	int goal = -1;
+	for (size_t i = 0; i < px.size(); ++i) {
+		int mx, my;
+		if (world_to_map(px[i], py[i], mx, my) && cells[(size_t)my * sx + mx] != 255) {
+			if (local_goal) goal = my * sx + mx;
+			else seeds.push_back(my * sx + mx);
+			started = true;
+		} else if (started) {
+			break;
+		}
+	}
+	if (local_goal && goal >= 0) seeds.push_back(goal);
+}
+
+// Replaces MapGridCostFunction::setTargetPoses + prepare(): seeds on the host (collect_seeds), wave front on the device.
 int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, int32_t n_plan, int32_t local_goal,
                         double highest_valid_cost_prev) {
 	if (!ctx || grid < 0 || grid >= HMP_NUM_MAPGRIDS || n_plan < 0 || (n_plan > 0 && !plan_xy)) {
@@ -931,58 +993,18 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 	CU(cudaSetDevice(ctx->device));
 	const int sx = ctx->size_x, sy = ctx->size_y;
 	const size_t n = (size_t)sx * sy;
-	if ((n + 31) / 32 * 4 > 200 * 1024) {
-		set_err("costmap too large for the on-device wave front");
+	if (hmp_dev_wavefront_smem(sx, sy, 1) > ctx->max_smem_optin) {   // mark bits + both frontier queues
+		set_err("costmap too large for the on-device wave front (%zu bytes of shared memory needed, %zu available)",
+		        hmp_dev_wavefront_smem(sx, sy, 1), ctx->max_smem_optin);
 		return HMP_E_CAPACITY;
 	}
-	auto world_to_map = [&](double wx, double wy, int& mx, int& my) {
-		if (wx < ctx->origin_x || wy < ctx->origin_y) return false;
-		mx = (int)((wx - ctx->origin_x) / ctx->resolution);
-		my = (int)((wy - ctx->origin_y) / ctx->resolution);
-		return mx < sx && my < sy;
-	};
 	// the costmap cells are needed for the NO_INFORMATION test of the seeds: keep a host copy from hmp_set_costmap
 	if (ctx->h_cells.size() != n) {
 		set_err("host copy of the costmap is missing");
 		return HMP_E_NOT_READY;
 	}
 	std::vector<int> seeds;
-	if (n_plan > 0) {
-		std::vector<double> px, py;
-		double last_x = plan_xy[0], last_y = plan_xy[1];
-		px.push_back(last_x);
-		py.push_back(last_y);
-		const double min_sq = ctx->resolution * ctx->resolution;
-		for (int i = 1; i < n_plan; ++i) {
-			double lx = plan_xy[2 * i], ly = plan_xy[2 * i + 1];
-			double sq = (lx - last_x) * (lx - last_x) + (ly - last_y) * (ly - last_y);
-			if (sq > min_sq) {
-				int steps = (int)std::ceil(std::sqrt(sq) / ctx->resolution);
-				double dx = (lx - last_x) / steps, dy = (ly - last_y) / steps;
-				for (int j = 1; j < steps; ++j) {
-					px.push_back(last_x + j * dx);
-					py.push_back(last_y + j * dy);
-				}
-			}
-			px.push_back(lx);
-			py.push_back(ly);
-			last_x = lx;
-			last_y = ly;
-		}
-		bool started = false;
-		int goal = -1;
-		for (size_t i = 0; i < px.size(); ++i) {
-			int mx, my;
-			if (world_to_map(px[i], py[i], mx, my) && ctx->h_cells[(size_t)my * sx + mx] != 255) {
-				if (local_goal) goal = my * sx + mx;
-				else seeds.push_back(my * sx + mx);
-				started = true;
-			} else if (started) {
-				break;
-			}
-		}
-		if (local_goal && goal >= 0) seeds.push_back(goal);
-	}
+	collect_seeds(ctx, ctx->h_cells.data(), plan_xy, n_plan, local_goal, seeds);
 	// per-slot staging so that the four grids of a cycle queue on the stream without a host synchronisation:
 	// [0] overflow status, [1..] seed cells
 	const size_t need = (1 + std::max<size_t>(1, seeds.size())) * sizeof(int);
@@ -1011,6 +1033,7 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 	ctx->wavefront_pending[grid] = true;
 	ctx->n_seeds[grid] = (int)seeds.size();   // overflow status is checked (and the scan kernel re-run) before the next plan
 	ctx->have_grid[grid] = true;
+	ctx->batch_grid_scenes = 0;
 	ctx->hv_prev[grid] = highest_valid_cost_prev;
 	ctx->last_valid = false;
 	return HMP_OK;
@@ -1080,12 +1103,15 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	const size_t det_bytes = (det_doubles * sizeof(double) + 8) * NS;
 	if ((rc = ctx->d_detail.ensure(det_bytes))) return rc;
 	if ((rc = ctx->h_out.ensure(det_bytes + cl.total))) return rc;
+	ctx->last_explain_n = 0;   // h_out is reused below
 
 	int blocks_x = 0, in_smem = 0, sweep_mode = 0;
 	size_t smem = 0, smem_sweep = 0;
 	if ((rc = launch_main(ctx, D, pl, &blocks_x, &smem, &in_smem, &sweep_mode, &smem_sweep))) return rc;
 	ctx->last_sweep_mode = sweep_mode;
-	if ((rc = ctx->d_block_best.ensure((size_t)NS * blocks_x * 2 * sizeof(unsigned long long)))) return rc;
+	// per-block argmin scratch: the main sweep's blocks, then (its own region) the blocks of the equisampled sweep
+	const int equi_blocks = D.n_equi > 0 ? (D.n_equi + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK : 0;
+	if ((rc = ctx->d_block_best.ensure((size_t)NS * ((size_t)blocks_x + equi_blocks) * 2 * sizeof(unsigned long long)))) return rc;
 
 	cudaStream_t st = ctx->stream;
 	CU(cudaMemcpyAsync(ctx->d_params.p, &D, sizeof(DevParams), cudaMemcpyHostToDevice, st));
@@ -1142,7 +1168,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		E.n_work = D.n_equi;
 		E.cand_offset = D.n_social;
 		E.best_out = (double*)(ctrl + cl.off_best2);
-		CU(hmp_dev_launch_plan(&E, (D.n_equi + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 2, smem, st));
+		E.block_best = A.block_best + (size_t)NS * blocks_x * 2;
+		CU(hmp_dev_launch_plan(&E, equi_blocks, 2, smem, st));
 		ctx->launches++;
 		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
 		A.best_init = E.best_out;
@@ -1162,6 +1189,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	B.totals = B.d_poses + (size_t)NS * T * 3;
 	B.d_nposes = (int32_t*)(B.totals + NS);
 	B.d_forces = nullptr;
+	std::function<int(int, const int32_t*)> refine_round;   // set in mode 2; also drives the fallback rounds below
+	int32_t* r_count_dev[2] = {nullptr, nullptr};
 	if (ctx->precise != 2) {
 		// winner's detail pass: one warp per scene re-runs the best candidate with write-back
 		B.n_work = 1;
@@ -1182,8 +1211,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const int rounds = (NS == 1 && ctx->refine_rounds >= 2) ? 2 : 1;
 		if ((rc = ctx->d_refine.ensure(r_set * rounds + 2 * NS * sizeof(double)))) return rc;   // + (threshold, effective window) of round 1
 		double* r_thr = (double*)((unsigned char*)ctx->d_refine.p + r_set * rounds);
-		int32_t* r_count_dev[2] = {nullptr, nullptr};
-		auto refine_round = [&](int round) -> int {
+		refine_round = [=, &r_count_dev](int round, const int32_t* active) -> int {
 			unsigned char* base = (unsigned char*)ctx->d_refine.p + r_set * round;
 			double* r_costs = (double*)base;
 			double* r_seeds = r_costs + nk * HMP_NUM_COSTS;
@@ -1193,7 +1221,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			int32_t* r_nposes = r_leaders + nk;
 			int32_t* r_count = r_nposes + nk;
 			CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
-			                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, st));
+			                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, active, st));
 			KernelArgs Rf = A;
 			Rf.precise = 1;
 			Rf.cand_list = r_leaders;
@@ -1222,7 +1250,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 				CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
 			}
 			CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
-			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, st));
+			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, active, st));
 			ctx->launches += 3;
 			r_count_dev[round] = r_count;   // read back after the last round (a copy to pageable memory here would stall the
 			                                // host, and with it the launches of the next round, until this round has finished)
@@ -1234,24 +1262,57 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		// round 2 every candidate whose FP32 total lies within the window of the final (FP64) best has been refined.
 		// The work ticket is reset between the rounds (both rollouts pull candidates from it).
 		ctx->last_n_leaders2 = 0;
-		if ((rc = refine_round(0))) return rc;
+		if ((rc = refine_round(0, nullptr))) return rc;
 		if (rounds == 2) {
 			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
-			if ((rc = refine_round(1))) return rc;
+			if ((rc = refine_round(1, nullptr))) return rc;
 		}
 		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 		if (r_count_dev[1]) CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
 	CU(cudaEventRecord(ctx->ev1, st));
-	CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
-	if (ctx->precise == 2)   // the refinement may have replaced (best total, best index) after the control-block snapshot
-		CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes + cl.off_best, ctrl + cl.off_best, (size_t)NS * 2 * sizeof(double),
-		                   cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
+	auto read_back = [&]() -> int {
+		CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
+		if (ctx->precise == 2)   // the refinement may have replaced (best total, best index) after the control-block snapshot
+			CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes + cl.off_best, ctrl + cl.off_best, (size_t)NS * 2 * sizeof(double),
+			                   cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		return HMP_OK;
+	};
+	if ((rc = read_back())) return rc;
 	float ms = 0.f;
 	CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	float ms_main = 0.f;
 	CU(cudaEventElapsedTime(&ms_main, ctx->ev0, ctx->evm));
+
+	ctx->last_fallback_rounds = 0;
+	std::vector<int32_t> unresolved(NS, 0);
+	if (ctx->precise == 2) {
+		// A scene is UNRESOLVED when the authoritative FP64 evaluation rejected every leader (the published record is the FP32
+		// best's, with a negative FP64 total): the FP32 selection must not be handed out. The refined (negative) totals are in
+		// the explored-totals array by now, so the best of the remaining valid totals becomes the new FP32 best and another
+		// refinement round runs around it -- until a refined winner exists, no valid candidate is left, or 8 rounds have passed
+		// (then the scene reports "no valid trajectory", the conservative answer). Rare: costs one host round trip per round.
+		const double* h_tot = (const double*)ctx->h_out.p + (size_t)NS * (HMP_NUM_COSTS + 3 + (size_t)T * 3);
+		const double* h_b = (const double*)((const unsigned char*)ctx->h_out.p + det_bytes + cl.off_best);
+		for (int iter = 0; iter < 8; ++iter) {
+			bool any = false;
+			for (int s = 0; s < NS; ++s) {
+				unresolved[s] = ((int)h_b[2 * s + 1] >= 0 && h_tot[s] < 0.0) ? 1 : 0;
+				any |= unresolved[s] != 0;
+			}
+			if (!any) break;
+			if ((rc = ctx->d_mask.ensure((size_t)NS * sizeof(int32_t)))) return rc;
+			CU(cudaMemcpyAsync(ctx->d_mask.p, unresolved.data(), (size_t)NS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+			CU(hmp_dev_launch_reselect(A.totals, C, A.best_out, (const int32_t*)ctx->d_mask.p, NS, st));
+			ctx->launches++;
+			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
+			if ((rc = refine_round(0, (const int32_t*)ctx->d_mask.p))) return rc;
+			if ((rc = read_back())) return rc;
+			ctx->last_fallback_rounds = iter + 1;
+		}
+		for (int s = 0; s < NS; ++s) unresolved[s] = ((int)h_b[2 * s + 1] >= 0 && h_tot[s] < 0.0) ? 1 : 0;
+	}
 
 	const double* h_det = (const double*)ctx->h_out.p;
 	const double* h_costs = h_det;
@@ -1266,6 +1327,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		HmpResult& r = results[s];
 		std::memset(&r, 0, sizeof(r));
 		int best = (int)h_best[2 * s + 1];
+		if (unresolved[s]) best = -1;   // FP64 rejected every candidate the fallback rounds reached
 		r.best_index = best;
 		r.status = best >= 0 ? 0 : 1;
 		r.n_candidates = C;
@@ -1366,6 +1428,144 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 	return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
 }
 
+// Uploads the per-scene costmaps of a batch (scene s = cells + s * size_x * size_y) into the padded device layout.
+static int upload_batch_costmaps(HmpContext* ctx, const uint8_t* cells, int n_scenes) {
+	const size_t n = (size_t)ctx->size_x * ctx->size_y;
+	int rc;
+	if ((rc = ctx->d_costmaps.ensure((size_t)ctx->costmap_stride * n_scenes))) return rc;
+	CU(cudaMemcpy2DAsync(ctx->d_costmaps.p, ctx->costmap_stride, cells, n, n, n_scenes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->h_cells.assign(cells, cells + n);   // scene 0 is what a later single-scene call sees
+	ctx->costmap_scenes = n_scenes;
+	ctx->dilated_dirty = true;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+// MapGridCostFunction::setTargetPoses + prepare() for n_scenes x 4 grids in ONE launch: seeds on the host, the wave fronts on
+// the device (one block per grid, mapgrid_wavefront_batch_kernel), so that a batch uploads 1 byte per cell (the costmap)
+// instead of 17 (costmap + four float grids).
+int hmp_compute_mapgrid_batch(HmpContext* ctx, int32_t n_scenes, const uint8_t* cells, const double* const plan_xy[HMP_NUM_MAPGRIDS],
+                              const int32_t* const plan_start[HMP_NUM_MAPGRIDS], const int32_t local_goal[HMP_NUM_MAPGRIDS]) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (n_scenes <= 0 || !plan_xy || !plan_start || !local_goal) {
+		set_err("bad batch mapgrid arguments");
+		return HMP_E_INVALID;
+	}
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!plan_xy[g] || !plan_start[g]) {
+			set_err("plan_xy[%d] / plan_start[%d] is null", g, g);
+			return HMP_E_INVALID;
+		}
+		for (int s = 0; s < n_scenes; ++s)
+			if (plan_start[g][s] < 0 || plan_start[g][s + 1] < plan_start[g][s]) {
+				set_err("plan_start[%d] is not a non-decreasing prefix array at scene %d", g, s);
+				return HMP_E_INVALID;
+			}
+	}
+	CU(cudaSetDevice(ctx->device));
+	if ((rc = resolve_wavefronts(ctx))) return rc;
+	const int sx = ctx->size_x, sy = ctx->size_y;
+	const size_t n = (size_t)sx * sy;
+	if (hmp_dev_wavefront_smem(sx, sy, 1) > ctx->max_smem_optin) {
+		set_err("costmap too large for the on-device wave front");
+		return HMP_E_CAPACITY;
+	}
+	if (cells) {
+		if ((rc = upload_batch_costmaps(ctx, cells, n_scenes))) return rc;
+	} else if (ctx->costmap_scenes < n_scenes) {
+		set_err("hmp_compute_mapgrid_batch needs the per-scene costmap cells (%d scenes resident, %d asked)", ctx->costmap_scenes, n_scenes);
+		return HMP_E_NOT_READY;
+	}
+	// seeds of all (scene, grid) pairs on the host threads: [status n_items][offsets n_items + 1][seeds ...]
+	const size_t items = (size_t)n_scenes * HMP_NUM_MAPGRIDS;
+	std::vector<std::vector<int>> seeds(items);
+	std::vector<uint8_t> cells_dev;   // only when the cells are not passed again (seed test needs them): read back
+	const uint8_t* cells_h = cells;
+	if (!cells_h) {
+		cells_dev.resize(n * n_scenes);
+		CU(cudaMemcpy2D(cells_dev.data(), n, ctx->d_costmaps.p, ctx->costmap_stride, n, n_scenes, cudaMemcpyDeviceToHost));
+		cells_h = cells_dev.data();
+	}
+	{
+		const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), items / 64 + 1));
+		auto work = [&](unsigned t) {
+			for (size_t it = t; it < items; it += nt) {
+				const int s = (int)(it / HMP_NUM_MAPGRIDS), g = (int)(it % HMP_NUM_MAPGRIDS);
+				const int a = plan_start[g][s], b = plan_start[g][s + 1];
+				collect_seeds(ctx, cells_h + (size_t)s * n, plan_xy[g] + 2 * (size_t)a, b - a, local_goal[g], seeds[it]);
+			}
+		};
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+		work(0);
+		for (auto& th : pool) th.join();
+	}
+	size_t total = 0;
+	for (auto& v : seeds) total += v.size();
+	const size_t words = items + (items + 1) + std::max<size_t>(1, total);
+	if ((rc = ctx->d_seeds[0].ensure(words * sizeof(int)))) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	if ((rc = ctx->h_seeds[0].ensure(words * sizeof(int)))) return rc;
+	int* hs = (int*)ctx->h_seeds[0].p;
+	std::memset(hs, 0, items * sizeof(int));
+	int* off = hs + items;
+	int* sd = off + items + 1;
+	size_t pos = 0;
+	for (size_t it = 0; it < items; ++it) {
+		off[it] = (int)pos;
+		if (!seeds[it].empty()) std::memcpy(sd + pos, seeds[it].data(), seeds[it].size() * sizeof(int));
+		pos += seeds[it].size();
+	}
+	off[items] = (int)pos;
+	if ((rc = ctx->d_mapgrids.ensure(n * HMP_NUM_MAPGRIDS * sizeof(float) * n_scenes))) return rc;
+	cudaStream_t st = ctx->stream;
+	int* d = (int*)ctx->d_seeds[0].p;
+	CU(cudaMemcpyAsync(d, hs, words * sizeof(int), cudaMemcpyHostToDevice, st));
+	CU(hmp_dev_launch_wavefront_batch((const uint8_t*)ctx->d_costmaps.p, ctx->costmap_stride, sx, sy, d + items + (items + 1), d + items,
+	                                  (float*)ctx->d_mapgrids.p, d, n_scenes, st));
+	ctx->launches++;
+	CU(cudaMemcpyAsync(hs, d, items * sizeof(int), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	for (size_t it = 0; it < items; ++it) {
+		if (!hs[it]) continue;   // frontier queue overflowed: redo this grid with the scan-based kernel
+		const int s = (int)(it / HMP_NUM_MAPGRIDS);
+		CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p + (size_t)s * ctx->costmap_stride, sx, sy, d + items + (items + 1) + off[it],
+		                            off[it + 1] - off[it], (float*)ctx->d_mapgrids.p + it * n, st));
+		ctx->launches++;
+	}
+	CU(cudaStreamSynchronize(st));
+	for (bool& b : ctx->have_grid) b = true;
+	ctx->batch_grid_scenes = n_scenes;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
+// Uploads n_scenes x 4 wave-front grids that are already FLOAT (cell counts are exact in FP32 below 2^24) straight from the
+// caller's buffers -- pinned memory makes the copy asynchronous at full PCIe rate -- without the double -> float pass of
+// hmp_plan_batch's target_dist argument. Values are the caller's responsibility here (hmp_set_mapgrid states the contract).
+int hmp_set_mapgrids_batch_f32(HmpContext* ctx, int32_t n_scenes, const float* const target_dist[HMP_NUM_MAPGRIDS]) {
+	int rc = check_ready(ctx);
+	if (rc) return rc;
+	if (n_scenes <= 0 || !target_dist || !target_dist[0] || !target_dist[1] || !target_dist[2] || !target_dist[3]) {
+		set_err("bad batch mapgrid arguments");
+		return HMP_E_INVALID;
+	}
+	CU(cudaSetDevice(ctx->device));
+	if ((rc = resolve_wavefronts(ctx))) return rc;
+	const size_t n = (size_t)ctx->size_x * ctx->size_y;
+	if ((rc = ctx->d_mapgrids.ensure(n * HMP_NUM_MAPGRIDS * sizeof(float) * n_scenes))) return rc;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g)   // [scene][grid][cells] on the device, [scene][cells] per grid on the host
+		CU(cudaMemcpy2DAsync((float*)ctx->d_mapgrids.p + (size_t)g * n, n * HMP_NUM_MAPGRIDS * sizeof(float), target_dist[g], n * sizeof(float),
+		                     n * sizeof(float), n_scenes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (bool& b : ctx->have_grid) b = true;
+	ctx->batch_grid_scenes = n_scenes;
+	ctx->last_valid = false;
+	return HMP_OK;
+}
+
 int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, const uint8_t* cells,
                    const double* const target_dist[HMP_NUM_MAPGRIDS], const double* highest_valid_cost_prev,
                    const HmpSampling* sampling, HmpResult* results) {
@@ -1375,7 +1575,12 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		set_err("bad batch arguments");
 		return HMP_E_INVALID;
 	}
+	if (!ctx->have_footprint && ctx->params.costs.scale[HMP_COST_OBSTACLE] != 0.0) {
+		set_err("hmp_set_footprint has not been called");
+		return HMP_E_NOT_READY;
+	}
 	CU(cudaSetDevice(ctx->device));
+	if ((rc = resolve_wavefronts(ctx))) return rc;   // device wave fronts of single-scene calls still in flight
 	const size_t n = (size_t)ctx->size_x * ctx->size_y;
 	int T = -1;
 	size_t stride = 0;
@@ -1393,15 +1598,33 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		set_err("rollout has %d steps, supported 1..%d", T, HMP_MAX_STEPS);
 		return HMP_E_CAPACITY;
 	}
+	// what the kernels will index must be resident for EVERY scene: costmaps and (if a MapGrid critic is on) the four grids
+	const bool any_grid = target_dist && (target_dist[0] || target_dist[1] || target_dist[2] || target_dist[3]);
+	if (any_grid) {
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+			if (!target_dist[g]) {
+				set_err("target_dist[%d] is null", g);
+				return HMP_E_INVALID;
+			}
+		}
+	} else {
+		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+			if (ctx->params.costs.scale[HMP_COST_PATH + g] == 0.0) continue;
+			if (n_scenes == 1 ? !ctx->have_grid[g] : ctx->batch_grid_scenes < n_scenes) {
+				set_err("MapGrid %d is not resident for %d scene(s): pass target_dist or call hmp_compute_mapgrid_batch / hmp_set_mapgrids_batch_f32 first", g,
+				        n_scenes);
+				return HMP_E_NOT_READY;
+			}
+		}
+	}
+	if (!cells && ctx->costmap_scenes < n_scenes) {
+		set_err("hmp_plan_batch needs per-scene costmap cells (%d scene(s) resident, %d asked)", ctx->costmap_scenes, n_scenes);
+		return HMP_E_INVALID;
+	}
 	DevParams D;
 	std::vector<double> amp_table;
 	if ((rc = build_dev_params(ctx, sampling, 0, T, D, amp_table))) return rc;
 	if ((rc = ctx->d_scenes.ensure(stride * n_scenes))) return rc;
-	// new per-scene costmaps / mapgrids replace the single-scene ones
-	if (cells) {
-		if ((rc = ctx->d_costmaps.ensure((size_t)ctx->costmap_stride * n_scenes))) return rc;
-	}
-	bool any_grid = target_dist && (target_dist[0] || target_dist[1] || target_dist[2] || target_dist[3]);
 	if (any_grid) {
 		if ((rc = ctx->d_mapgrids.ensure(n * HMP_NUM_MAPGRIDS * sizeof(float) * n_scenes))) return rc;
 	}
@@ -1410,29 +1633,27 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 	CU(cudaStreamSynchronize(ctx->stream));
 	unsigned char* hs = (unsigned char*)ctx->h_stage.p;
 	std::memset(hs, 0, stride * n_scenes);
-	for (int s = 0; s < n_scenes; ++s) {
-		pack_scene(ctx, worlds[s], highest_valid_cost_prev ? highest_valid_cost_prev + 4 * (size_t)s : nullptr, D.dt_d,
-		           hs + stride * s);
+	{
+		// scene blobs packed by the host threads (a 4096-world batch is ~12 MB of records)
+		const unsigned nt = (unsigned)std::max(1, std::min<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), n_scenes / 64 + 1));
+		auto work = [&](unsigned t) {
+			for (int s = (int)t; s < n_scenes; s += (int)nt)
+				pack_scene(ctx, worlds[s], highest_valid_cost_prev ? highest_valid_cost_prev + 4 * (size_t)s : nullptr, D.dt_d, hs + stride * s);
+		};
+		std::vector<std::thread> pool;
+		for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+		work(0);
+		for (auto& th : pool) th.join();
 	}
 	CU(cudaMemcpyAsync(ctx->d_scenes.p, hs, stride * n_scenes, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	if (cells) {
-		CU(cudaMemcpy2DAsync(ctx->d_costmaps.p, ctx->costmap_stride, cells, n, n, n_scenes, cudaMemcpyHostToDevice, ctx->stream));
-		CU(cudaStreamSynchronize(ctx->stream));
-		ctx->dilated_dirty = true;
-	} else if (n_scenes > 1) {
-		set_err("hmp_plan_batch needs per-scene costmap cells");
-		return HMP_E_INVALID;
+		if ((rc = upload_batch_costmaps(ctx, cells, n_scenes))) return rc;
 	}
 	if (any_grid) {
-		for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
-			if (!target_dist[g]) {
-				set_err("target_dist[%d] is null", g);
-				return HMP_E_INVALID;
-			}
-		}
 		// double -> float conversion of n_scenes x 4 grids (328 MB for 512 scenes of 200 x 200) by all host threads into two
-		// pinned staging buffers; the copy of one chunk of scenes overlaps the conversion of the next
+		// pinned staging buffers; the copy of one chunk of scenes overlaps the conversion of the next. Values must be cell
+		// counts in [0, size_x * size_y + 1] (the contract of hmp_set_mapgrid), checked on the way.
 		const size_t scene_floats = n * HMP_NUM_MAPGRIDS;
 		const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_scenes, ((size_t)48 << 20) / (scene_floats * sizeof(float))));
 		if ((rc = ctx->h_grid_stage[0].ensure((size_t)chunk * scene_floats * sizeof(float)))) return rc;
@@ -1440,30 +1661,50 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		for (int b = 0; b < 2; ++b)
 			if (!ctx->grid_stage_ev[b]) CU(cudaEventCreateWithFlags(&ctx->grid_stage_ev[b], cudaEventDisableTiming));
 		const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		const double limit = (double)n + 1.0;
 		int buf = 0;
+		int bad_any = 0;
 		for (int s0 = 0; s0 < n_scenes; s0 += chunk, buf ^= 1) {
 			const int ns = std::min(chunk, n_scenes - s0);
 			if (s0 >= 2 * chunk) CU(cudaEventSynchronize(ctx->grid_stage_ev[buf]));   // the copy that last read this buffer
 			float* f = (float*)ctx->h_grid_stage[buf].p;
 			const size_t items = (size_t)ns * HMP_NUM_MAPGRIDS;   // (scene, grid) pairs of this chunk
 			const unsigned nt = (unsigned)std::min<size_t>(hw, items);
+			std::vector<int> bad_t(nt, 0);
 			auto work = [&](unsigned t) {
+				int bad = 0;
 				for (size_t it = t; it < items; it += nt) {
 					const int s = s0 + (int)(it / HMP_NUM_MAPGRIDS), g = (int)(it % HMP_NUM_MAPGRIDS);
 					const double* src = target_dist[g] + (size_t)s * n;
 					float* dst = f + it * n;
-					for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+					for (size_t i = 0; i < n; ++i) {
+						const double v = src[i];
+						const int iv = (int)v;   // NaN / out-of-range convert to INT_MIN on x86-64 and fail the round trip
+						bad |= ((double)iv != v) | (iv < 0) | (v > limit);
+						dst[i] = (float)iv;
+					}
 				}
+				bad_t[t] = bad;
 			};
 			std::vector<std::thread> pool;
 			for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
 			work(0);
 			for (auto& th : pool) th.join();
+			for (int b : bad_t) bad_any |= b;
+			if (bad_any) break;
 			CU(cudaMemcpyAsync((float*)ctx->d_mapgrids.p + (size_t)s0 * scene_floats, f, items * n * sizeof(float), cudaMemcpyHostToDevice,
 			                   ctx->stream));
 			CU(cudaEventRecord(ctx->grid_stage_ev[buf], ctx->stream));
 		}
+		if (bad_any) {
+			CU(cudaStreamSynchronize(ctx->stream));
+			ctx->batch_grid_scenes = 0;
+			for (bool& b : ctx->have_grid) b = false;
+			set_err("a target_dist value is not a cell count in [0, size_x*size_y+1]");
+			return HMP_E_INVALID;
+		}
 		for (bool& b : ctx->have_grid) b = true;
+		ctx->batch_grid_scenes = n_scenes;
 	}
 	PlanLaunch pl{n_scenes, (uint32_t)stride, 0, T};
 	return run_cycle(ctx, D, amp_table, nullptr, 0, std::vector<double>(), pl, results, nullptr, 0);
@@ -1471,10 +1712,14 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 
 // Re-runs the selection of the last plan on the data still resident on the device (no host<->device
 // traffic except the 16-byte result): used to time the kernels with inputs already in HBM.
-int hmp_replan_resident(HmpContext* ctx, HmpResult* results) {
+int hmp_replan_resident(HmpContext* ctx, HmpResult* results, int32_t results_capacity) {
 	if (!ctx || !results || !ctx->last_valid) {
 		set_err("no previous plan to re-run");
 		return HMP_E_NOT_READY;
+	}
+	if (results_capacity < ctx->last_n_scenes) {
+		set_err("results holds %d records, the last plan had %d scenes", results_capacity, ctx->last_n_scenes);
+		return HMP_E_INVALID;
 	}
 	CU(cudaSetDevice(ctx->device));
 	PlanLaunch pl{ctx->last_n_scenes, ctx->last_scene_stride, (int)ctx->last_extra.size(), ctx->last_T};
@@ -1562,6 +1807,8 @@ int hmp_explain(HmpContext* ctx, const int32_t* candidate_indices, int32_t n, do
 	if (seeds_out) std::memcpy(seeds_out, h + (size_t)n * HMP_NUM_COSTS, (size_t)n * 3 * sizeof(double));
 	if (poses_out) std::memcpy(poses_out, h + (size_t)n * (HMP_NUM_COSTS + 3), (size_t)n * T * 3 * sizeof(double));
 	if (n_steps_out) std::memcpy(n_steps_out, (const int32_t*)(h + doubles) + n, (size_t)n * sizeof(int32_t));
+	ctx->last_explain_n = n;   // h_out holds this call's forces until another call reuses it (hmp_debug_last_forces)
+	ctx->last_explain_T = T;
 	return HMP_OK;
 }
 
@@ -1571,6 +1818,11 @@ int hmp_debug_last_forces(HmpContext* ctx, int32_t n, double* forces_out) {
 	if (!ctx || !forces_out || !ctx->last_valid || n <= 0) {
 		set_err("bad arguments");
 		return HMP_E_INVALID;
+	}
+	if (n != ctx->last_explain_n || ctx->last_dev_params.T != ctx->last_explain_T) {
+		set_err("the last hmp_explain call covered %d candidates x %d steps, not %d x %d (or another call reused its buffer)",
+		        ctx->last_explain_n, ctx->last_explain_T, n, ctx->last_dev_params.T);
+		return HMP_E_NOT_READY;
 	}
 	const int T = ctx->last_dev_params.T;
 	const double* h = (const double*)ctx->h_out.p;
@@ -2033,6 +2285,10 @@ int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders) 
 int hmp_last_num_leaders(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders : -1; }
 
 int hmp_last_num_leaders_round2(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders2 : -1; }
+
+int hmp_last_fallback_rounds(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_fallback_rounds : -1; }
+
+int hmp_last_num_scenes(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_scenes : -1; }
 
 int64_t hmp_launch_count(HmpContext* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -148,8 +148,9 @@ CONFIGS = {
 
 
 def make_scene(cfg: CycleConfig, seed: int, robot_xy=(0.0, 0.0), robot_yaw: float = 0.0,
-               base_vel=(0.3, 0.0, 0.0)) -> Scene:
-    """Seeded synthetic World + costmap + MapGrids + footprint for one planning cycle."""
+               base_vel=(0.3, 0.0, 0.0), with_grids: bool = True) -> Scene:
+    """Seeded synthetic World + costmap + MapGrids + footprint for one planning cycle. with_grids=False skips the host wave
+    fronts (Scene.grids is empty; Scene.plans holds what hmp_compute_mapgrid[_batch] needs to compute them on the device)."""
     rng = np.random.default_rng(seed)
     res, n = cfg.resolution, cfg.size
     rx, ry = robot_xy
@@ -256,7 +257,7 @@ def make_scene(cfg: CycleConfig, seed: int, robot_xy=(0.0, 0.0), robot_yaw: floa
         mapgrid_wavefront(cells, origin_x, origin_y, res, plan, True),         # goal_costs_ (local goal)
         mapgrid_wavefront(cells, origin_x, origin_y, res, plan, False),        # alignment_costs_
         mapgrid_wavefront(cells, origin_x, origin_y, res, front_plan, True),   # goal_front_costs_ (local goal)
-    ]
+    ] if with_grids else []
 
     w = HmpWorld()
     w.robot_x, w.robot_y, w.robot_yaw = rx, ry, robot_yaw

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HMP_ABI_VERSION 1
+#define HMP_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 #define HMP_OK            0
@@ -331,6 +331,11 @@ int hmp_last_num_leaders(HmpContext* ctx);
  * lies within the window of the final (FP64) best has been re-scored even when the FP32 best was a rollout with a large
  * FP32 error. Returns how many candidates that second round re-scored in the last plan (almost always 0). */
 int hmp_last_num_leaders_round2(HmpContext* ctx);
+/* Mode 2: when the FP64 evaluation rejects EVERY leader (e.g. the footprint of each touches a lethal cell by a margin FP32
+ * missed), the FP32 selection is not handed out: the best of the remaining valid FP32 totals is taken and refined, up to 8
+ * more rounds; if none yields a valid FP64 winner the plan reports status 1 / best_index -1 (no valid trajectory).
+ * Returns how many such extra rounds the last plan needed (0 almost always). */
+int hmp_last_fallback_rounds(HmpContext* ctx);
 /* Work layout of the FP32 sweep (modes 0 and 2): 0 (default) = automatic, 1 = one warp per candidate (lanes stride over the
  * objects; shortest latency for a few thousand candidates), 2 = one thread per candidate (a warp rolls out 32 candidates,
  * the per-step scalar section is issued once per 32; highest throughput from ~16k candidates per launch). Both layouts
@@ -377,16 +382,36 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 
 /* Same, for a batch of independent scenes that share params, costmap geometry and sampling but
  * have their own world, costmap cells and MapGrids (BASELINE config "batched scenes"). Scene s uses
- * worlds[s], cells + s * size_x * size_y, target_dist[g] + s * size_x * size_y. One launch. */
+ * worlds[s], cells + s * size_x * size_y, target_dist[g] + s * size_x * size_y. One launch.
+ * cells = NULL reuses the costmaps of an earlier batch call, target_dist = NULL the grids left resident by
+ * hmp_compute_mapgrid_batch / hmp_set_mapgrids_batch_f32 / an earlier batch; HMP_E_NOT_READY / HMP_E_INVALID if they do
+ * not cover n_scenes scenes. target_dist values are checked like hmp_set_mapgrid's. */
 int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes,
                    const uint8_t* cells, const double* const target_dist[HMP_NUM_MAPGRIDS],
                    const double* highest_valid_cost_prev /* [n_scenes][4] or NULL */,
                    const HmpSampling* sampling, HmpResult* results);
 
+/* Batch variant of hmp_compute_mapgrid (MapGridCostFunction::setTargetPoses + prepare(), src/map_grid_cost_function.cpp:63-79,
+ * for every scene of a batch): the four wave-front grids of n_scenes scenes are computed on the device in one launch from
+ * the per-scene costmaps and plans, and stay resident for the following hmp_plan_batch call (pass cells = NULL and
+ * target_dist = NULL there). cells: n_scenes costmaps (scene s = cells + s * size_x * size_y), or NULL to reuse the costmaps
+ * of an earlier batch call. plan_xy[g]: the poses (xy interleaved, map frame) of slot g of all scenes back to back;
+ * plan_start[g][s] .. plan_start[g][s + 1] is scene s's range of POSES in it (n_scenes + 1 entries). local_goal[g] =
+ * is_local_goal_function_ of slot g. This replaces the upload of 4 x 4 bytes per cell and scene by 1 byte per cell. */
+int hmp_compute_mapgrid_batch(HmpContext* ctx, int32_t n_scenes, const uint8_t* cells, const double* const plan_xy[HMP_NUM_MAPGRIDS],
+                              const int32_t* const plan_start[HMP_NUM_MAPGRIDS], const int32_t local_goal[HMP_NUM_MAPGRIDS]);
+/* Uploads the wave-front grids of a batch as FLOATS (cell counts are exact in FP32 below 2^24) straight from the caller's
+ * buffers, target_dist[g] + s * size_x * size_y = grid g of scene s; no conversion pass, full PCIe rate from pinned memory.
+ * They stay resident for hmp_plan_batch(..., target_dist = NULL, ...). */
+int hmp_set_mapgrids_batch_f32(HmpContext* ctx, int32_t n_scenes, const float* const target_dist[HMP_NUM_MAPGRIDS]);
+
 /* Re-runs the last hmp_plan / hmp_plan_batch on the scene data still resident in device memory (only
- * the few-KB parameter block is re-sent and the result read back). No reference counterpart: it exists so
- * that benchmarks can time the kernels with inputs already in HBM. */
-int hmp_replan_resident(HmpContext* ctx, HmpResult* results);
+ * the few-KB parameter block is re-sent and the result read back). `results` must hold results_capacity >=
+ * hmp_last_num_scenes() records. No reference counterpart: it exists so that benchmarks can time the kernels with inputs
+ * already in HBM. */
+int hmp_replan_resident(HmpContext* ctx, HmpResult* results, int32_t results_capacity);
+/* Scenes of the last plan (1 for hmp_plan), -1 if there is none. */
+int hmp_last_num_scenes(HmpContext* ctx);
 
 /* ---- diagnostics of the LAST hmp_plan (traj_explored_, humap_planner.cpp:1367,1969-2084) ------ */
 /* Weighted total per candidate (negative = reference error code); n must equal n_candidates. */

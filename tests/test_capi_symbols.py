@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load_library()
     for name in _declared_functions():
         assert hasattr(lib, name), name
-    assert lib.hmp_abi_version() == 1
+    assert lib.hmp_abi_version() == 2
 
 
 def test_struct_sizes_match_the_c_layout():

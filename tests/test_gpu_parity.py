@@ -188,6 +188,7 @@ def test_generator_rejections_and_codes(cycle):
     # candidates the generator rejected (-1), collisions (-6), off-map (-4): same code on both sides
     neg = (g < 0) | (o < 0)
     mism = neg & (g != o)
+    print(f"GATE codes {cycle['cfg'].name} precise={cycle['precise']}: {int(mism.sum())} of {len(g)} mismatches")
     assert mism.mean() <= 0.02, f"{int(mism.sum())} of {len(g)} candidates disagree on validity / error code"
     assert np.array_equal(cycle["ex"]["n_poses"] == cycle["T"], g != -1.0)
 
@@ -211,6 +212,8 @@ def _check_rollout_poses(cycle, ref):
     exy = np.abs(gp[..., :2] - op[..., :2]).max(axis=(1, 2))
     eyaw = _yaw_err(gp[..., 2], op[..., 2]).max(axis=1)
     ok = (exy <= POSE_TOL) & (eyaw <= POSE_TOL)
+    print(f"GATE poses {cycle['cfg'].name} precise={cycle['precise']}: share within tol {ok.mean():.4f} of {len(ok)}, max xy {exy.max():.2e} "
+          f"yaw {eyaw.max():.2e}, median xy {np.median(exy):.2e}")
     if cycle["precise"]:
         # FP64 object loops: the CUDA path reproduces the oracle's trajectories to rounding noise for EVERY candidate,
         # including the ill-conditioned ones -- the restatement itself is exact
@@ -254,6 +257,7 @@ def test_critics_on_device_poses(cycle):
         if total >= 0:
             assert _rel_err(gt, total) < 5e-4 or bad[7] > 0
     assert n > 0
+    print(f"GATE critics {cycle['cfg'].name} precise={cycle['precise']}: n={n} bad per critic {bad}")
     for k, b in bad.items():
         assert b <= max(1, 0.02 * n), f"{COST_NAMES[k]}: {b}/{n} trajectories outside 1e-4 relative"
 
@@ -305,6 +309,8 @@ def _check_totals(cycle, o):
     v = (g >= 0) & (o >= 0)
     assert v.sum() > 0
     rel = _rel_err(g[v], o[v])
+    print(f"GATE totals {cycle['cfg'].name} precise={cycle['precise']}: n={int(v.sum())} median {np.median(rel):.2e} within 1e-4 {(rel <= 1e-4).mean():.4f} "
+          f"above 1e-3 {int((rel > 1e-3).sum())} above 1e-2 {int((rel > 1e-2).sum())} max {rel.max():.2e}")
     # totals include cell-indexed critics: a pose difference of 1e-6 m can move a footprint vertex into the
     # neighbouring cell, so a small share of candidates differs by one cell's worth of cost
     assert np.median(rel) < 1e-5

@@ -31,6 +31,8 @@ cubin = os.path.join(tmp, "hmp_kernels.sm_100a.cubin")
 with open(os.path.join(out, f"{tag}_ncu_by_line.txt"), "w") as f:
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), page, cubin, "sweep_tpc", "60", "0", "hmp_sweep_tpc.inl"],
                    stdout=f, stderr=subprocess.STDOUT, cwd=ROOT)
+subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opcounts.py"), page, raw, os.path.join(out, f"{tag}_ncu_counts.json"),
+                f"ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 ({tag}), sweep_tpc_kernel"], check=True, stdout=subprocess.DEVNULL)
 rows = list(csv.reader(open(raw)))
 d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
