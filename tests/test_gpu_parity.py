@@ -189,7 +189,9 @@ def test_generator_rejections_and_codes(cycle):
     neg = (g < 0) | (o < 0)
     mism = neg & (g != o)
     print(f"GATE codes {cycle['cfg'].name} precise={cycle['precise']}: {int(mism.sum())} of {len(g)} mismatches")
-    assert mism.mean() <= 0.02, f"{int(mism.sum())} of {len(g)} candidates disagree on validity / error code"
+    # measured (r02a, GPUTEST log): 0 mismatches in every sampled cycle, 1-2 of 65 536 on the full cfg2 grid (test_gpu_headline);
+    # one borderline feasibility / cell test per sample is the allowance
+    assert mism.sum() <= 1, f"{int(mism.sum())} of {len(g)} candidates disagree on validity / error code"
     assert np.array_equal(cycle["ex"]["n_poses"] == cycle["T"], g != -1.0)
 
 
@@ -223,7 +225,8 @@ def _check_rollout_poses(cycle, ref):
         # amplified by the rollout dynamics (|F| / m per step); the bulk stays far inside the band, a bounded tail of
         # ill-conditioned candidates (amplified interaction forces of 1e3..1e6 N in the crowd-stress grid) leaves it
         # late in the horizon. DESIGN.md "precision" quantifies this per configuration.
-        floor = 0.90 if cycle["cfg"].name != "cfg2" else 0.85
+        # floors = the lowest share measured per configuration (r02a: cfg0 0.971, cfg1 0.988, cfg2 0.946) minus ~1.5 points
+        floor = {"cfg0": 0.955, "cfg1": 0.975, "cfg2": 0.93}[cycle["cfg"].name]
         assert ok.mean() >= floor, f"pose parity {ok.mean():.4f} (max xy {exy.max():.2e}, yaw {eyaw.max():.2e})"
         if cycle["cfg"].name != "cfg2":
             assert exy.max() < 5e-3 and eyaw.max() < 5e-3    # the tail stays bounded
@@ -255,11 +258,11 @@ def test_critics_on_device_poses(cycle):
                 bad[k] += int(_rel_err(g[k], raw[k]) > REL and abs(g[k] - raw[k]) > 1e-6)
         gt = cycle["totals"][cycle["idx"][j]]
         if total >= 0:
-            assert _rel_err(gt, total) < 5e-4 or bad[7] > 0
+            assert _rel_err(gt, total) < 1e-4, (j, gt, total)
     assert n > 0
     print(f"GATE critics {cycle['cfg'].name} precise={cycle['precise']}: n={n} bad per critic {bad}")
-    for k, b in bad.items():
-        assert b <= max(1, 0.02 * n), f"{COST_NAMES[k]}: {b}/{n} trajectories outside 1e-4 relative"
+    for k, b in bad.items():   # measured (r02a): 0 for every critic in every cycle; one trajectory is the allowance
+        assert b <= 1, f"{COST_NAMES[k]}: {b}/{n} trajectories outside 1e-4 relative"
 
 
 def test_totals_against_oracle(cycle):
@@ -274,7 +277,7 @@ def test_totals_and_critics_vs_reference_fixture(cycle):
     _check_totals(cycle, gold["totals"])
     g, o = cycle["totals"][cycle["idx"]], gold["totals"]
     neg = (g < 0) | (o < 0)
-    assert (neg & (g != o)).mean() <= 0.02
+    assert (neg & (g != o)).sum() <= 1
     if cycle["precise"]:
         # FP64 object loops: trajectories equal the reference's to rounding noise, so each critic can be compared on
         # its own trajectory: integer-valued critics exactly, the others within 1e-4 relative
@@ -287,10 +290,12 @@ def test_totals_and_critics_vs_reference_fixture(cycle):
             if not m.any():
                 continue
             if k <= 4:
-                assert (a[m] != b[m]).mean() <= 0.02, COST_NAMES[k]     # a vertex exactly on a cell edge may flip
+                print(f"GATE fixture-critic {cycle['cfg'].name} {COST_NAMES[k]}: {int((a[m] != b[m]).sum())} of {int(m.sum())} differ")
+                assert (a[m] != b[m]).sum() <= 1, COST_NAMES[k]     # a vertex exactly on a cell edge may flip
             else:
                 bad = (_rel_err(a[m], b[m]) > REL) & (np.abs(a[m] - b[m]) > 1e-6)
-                assert bad.mean() <= 0.02, (COST_NAMES[k], float(np.abs(a[m] - b[m]).max()))
+                print(f"GATE fixture-critic {cycle['cfg'].name} {COST_NAMES[k]}: {int(bad.sum())} of {int(m.sum())} outside 1e-4")
+                assert bad.sum() <= 1, (COST_NAMES[k], float(np.abs(a[m] - b[m]).max()))
     if "best_index" in gold and int(gold["best_index"]) >= 0 and len(o) == int(gold["C"]):
         # selection of the whole cycle (fixture: the reference's own early-exit loop): identical unless the reference's two
         # best totals are within 1e-4 relative
@@ -317,7 +322,9 @@ def _check_totals(cycle, o):
     if cycle["precise"]:
         assert rel.max() < 1e-5      # social critics are FP32 in both modes: ~1e-7 relative on O(1) terms
     else:
-        assert (rel > 1e-3).mean() <= (0.05 if cycle["cfg"].name != "cfg2" else 0.15)
+        # measured (r02a): every sampled candidate within 6.5e-5; on the full cfg2 grid 99.45 % within 1e-4 and 0.06 % above 1e-2
+        # (chaotic rollouts) -- test_gpu_headline holds the full-grid gates
+        assert (rel <= 1e-4).mean() >= 0.98 and (rel > 1e-2).sum() == 0
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
@@ -357,8 +364,9 @@ def test_selection_cfg1_full_grid(planner):
     assert res.best_index == best or top2_close or abs(res.best_total - full[best]) <= 1e-4 * abs(full[best])
     g = planner.explored_totals(res.n_candidates)
     agree = ((g < 0) & (full < 0) & (g == full)) | ((g >= 0) & (full >= 0))
-    assert agree.mean() > 0.995
-    assert abs(res.n_valid - len(valid)) <= 0.005 * len(full)
+    print(f"GATE cfg1-full-grid: {int((~agree).sum())} of {len(full)} disagree on validity / code, n_valid {res.n_valid} vs {len(valid)}")
+    assert (~agree).sum() <= 8     # measured: <= 3 of 16 384 (profiles/r01j_accuracy_totals.json)
+    assert abs(res.n_valid - len(valid)) <= 8
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -537,7 +545,8 @@ def test_parameter_variants(planner, mutate, precise, layout):
     assert (planner.last_sweep_mode() != 0) == (layout == 2 and not precise)
     planner.set_precision(False)
     g, o = cy["totals"][cy["idx"]], cy["orc"]["totals"]
-    assert ((g < 0) == (o < 0)).mean() >= (1.0 if precise else 0.97)
+    print(f"GATE variant precise={precise}: validity mismatches {int(((g < 0) != (o < 0)).sum())} of {len(g)}")
+    assert ((g < 0) != (o < 0)).sum() <= (0 if precise else 1)
     both_neg = (g < 0) & (o < 0)
     assert np.array_equal(g[both_neg], o[both_neg])
     T = cy["T"]
@@ -549,6 +558,7 @@ def test_parameter_variants(planner, mutate, precise, layout):
         if precise:
             assert exy.max() < 1e-8 and eyaw.max() < 1e-8, (exy.max(), eyaw.max())
         else:
+            print(f"GATE variant poses: share {((exy <= POSE_TOL) & (eyaw <= POSE_TOL)).mean():.4f} max {exy.max():.2e} {eyaw.max():.2e}")
             assert ((exy <= POSE_TOL) & (eyaw <= POSE_TOL)).mean() >= 0.90
             assert exy.max() < 5e-3 and eyaw.max() < 5e-3
         gc, oc = cy["ex"]["costs"][both], cy["orc"]["costs"][both]
