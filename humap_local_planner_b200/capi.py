@@ -120,14 +120,19 @@ class HmpShape(C.Structure):
                 ("radius", _d), ("vx", _d), ("vy", _d)]
 
 
+MAX_ENV_POLYGON = 16
+
+
 class HmpEnvParams(C.Structure):
     _fields_ = [("robot_model", _i), ("obstacles_closest_num", _i), ("people_closest_num", _i), ("groups_closest_num", _i),
                 ("robot_radius", _d), ("person_model_radius", _d), ("obstacle_extension_multiplier", _d),
                 ("ttc_collision_distance", _d), ("person_containment_rate", _d), ("obstacles_force_dynamic", _i),
-                ("people_force_dynamic", _i)]
+                ("people_force_dynamic", _i), ("two_circles", _d * 4), ("line_xy", _d * 4), ("n_polygon", _i), ("_pad", _i),
+                ("polygon_xy", _d * (2 * MAX_ENV_POLYGON))]
 
 
 SHAPE_POINT, SHAPE_CIRCLE, SHAPE_LINE, SHAPE_POLYGON = 0, 1, 2, 3
+ROBOT_POINT, ROBOT_CIRCULAR, ROBOT_TWO_CIRCLES, ROBOT_LINE, ROBOT_POLYGON = 0, 1, 2, 3, 4
 
 
 class HmpEquisampled(C.Structure):

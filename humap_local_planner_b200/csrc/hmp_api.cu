@@ -46,6 +46,8 @@ extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, 
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
                                                       int32_t* leaders, int32_t* count, const double* thr_lo, double* thr_out,
                                                       int min_leaders, int n_scenes, const int32_t* active, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_hv_early_exit(const double* totals, const double* hv_pre, const float* hv_val, int C,
+                                                    unsigned int* hv_out, int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_reselect(const double* totals, int C, double* best_out, const int32_t* active, int n_scenes,
                                                cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
@@ -201,7 +203,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec;
 	HostBuf h_stage, h_out;
 	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
@@ -776,7 +778,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->wf_done[g]) cudaEventDestroy(ctx->wf_done[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask, &ctx->d_hvrec};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	for (int b = 0; b < 2; ++b) {
@@ -1096,6 +1098,10 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	if ((rc = ctx->d_extra.ensure(std::max<size_t>(1, (size_t)n_extra) * sizeof(HmpSample)))) return rc;
 	if ((rc = ctx->d_equi.ensure(std::max<size_t>(1, equi.size()) * sizeof(double)))) return rc;
 	if ((rc = ctx->d_totals.ensure((size_t)NS * C * sizeof(double)))) return rc;
+	// per candidate and MapGrid critic: partial sum before the critic (f64) + largest valid cell value (f32), for the
+	// early-exit semantics of highest_valid_cost_ (hv_early_exit_kernel)
+	const size_t hv_items = (size_t)NS * C * HMP_NUM_MAPGRIDS;
+	if ((rc = ctx->d_hvrec.ensure(hv_items * (sizeof(double) + sizeof(float))))) return rc;
 	const CtrlLayout cl = ctrl_layout(NS);
 	if ((rc = ctx->d_ctrl.ensure(cl.total))) return rc;
 	// detail buffer per scene: costs[14] seeds[3] poses[T][3] totals[1] (f64) + nposes (i32, padded to 8)
@@ -1142,6 +1148,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.hv_out = (unsigned int*)(ctrl + cl.off_hv);
 	A.best_out = (double*)(ctrl + cl.off_best);
 	A.no_prune = ctx->prune_obstacle ? 0 : 1;
+	A.hv_pre = (double*)ctx->d_hvrec.p;
+	A.hv_val = (float*)((double*)ctx->d_hvrec.p + hv_items);
 
 	CU(cudaEventRecord(ctx->ev0, st));
 	// dilated max-cost map for the exact pruning of the obstacle critic (rebuilt when costmap / footprint / separation change)
@@ -1182,6 +1190,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 
 	KernelArgs B = A;
+	B.hv_pre = nullptr;   // detail / refinement launches do not record (the sweep's records stand)
+	B.hv_val = nullptr;
 	double* det = (double*)ctx->d_detail.p;
 	B.d_costs = det;
 	B.d_seeds = det + (size_t)NS * HMP_NUM_COSTS;
@@ -1223,6 +1233,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
 			                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, active, st));
 			KernelArgs Rf = A;
+			Rf.hv_pre = nullptr;
+			Rf.hv_val = nullptr;
 			Rf.precise = 1;
 			Rf.cand_list = r_leaders;
 			Rf.cand_list_stride = K;
@@ -1270,9 +1282,19 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 		if (r_count_dev[1]) CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
+	// highest_valid_cost_ of the MapGrid critics as the reference's sequential, early-exiting loop would leave it: needs the final
+	// explored totals (refined leaders included) for the best-so-far every candidate was scored against
+	auto hv_pass = [&]() -> int {
+		CU(hmp_dev_launch_hv_early_exit(A.totals, A.hv_pre, A.hv_val, C, A.hv_out, NS, st));
+		ctx->launches++;
+		return HMP_OK;
+	};
+	if ((rc = hv_pass())) return rc;
 	CU(cudaEventRecord(ctx->ev1, st));
 	auto read_back = [&]() -> int {
 		CU(cudaMemcpyAsync(ctx->h_out.p, det, det_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes + cl.off_hv, ctrl + cl.off_hv, (size_t)NS * 4 * sizeof(unsigned int),
+		                   cudaMemcpyDeviceToHost, st));
 		if (ctx->precise == 2)   // the refinement may have replaced (best total, best index) after the control-block snapshot
 			CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes + cl.off_best, ctrl + cl.off_best, (size_t)NS * 2 * sizeof(double),
 			                   cudaMemcpyDeviceToHost, st));
@@ -1308,6 +1330,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			ctx->launches++;
 			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 			if ((rc = refine_round(0, (const int32_t*)ctx->d_mask.p))) return rc;
+			if ((rc = hv_pass())) return rc;
 			if ((rc = read_back())) return rc;
 			ctx->last_fallback_rounds = iter + 1;
 		}
@@ -1967,8 +1990,12 @@ size_t align16(size_t v) { return (v + 15) / 16 * 16; }
 int env_select(HmpContext* ctx, const HmpEnvParams& env, const double robot_pose[3], const HmpShape* shapes, int n_shapes,
                const double* verts, int n_verts, const HmpPerson* people, int n_people, const HmpGroup* groups, int n_groups,
                int n_positions, EnvSelection& sel) {
-	if (env.robot_model != 0 && env.robot_model != 1) {
-		set_err("robot_model %d: only the point (0) and circular (1) footprint models are built", env.robot_model);
+	if (env.robot_model < HMP_ROBOT_POINT || env.robot_model > HMP_ROBOT_POLYGON) {
+		set_err("robot_model %d: unknown footprint model (0 point, 1 circular, 2 two circles, 3 line, 4 polygon)", env.robot_model);
+		return HMP_E_INVALID;
+	}
+	if (env.robot_model == HMP_ROBOT_POLYGON && (env.n_polygon < 1 || env.n_polygon > HMP_MAX_ENV_POLYGON)) {
+		set_err("polygon footprint model with %d vertices (1..%d supported)", env.n_polygon, HMP_MAX_ENV_POLYGON);
 		return HMP_E_INVALID;
 	}
 	for (int i = 0; i < n_shapes; ++i) {

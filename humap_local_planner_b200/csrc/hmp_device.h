@@ -198,6 +198,12 @@ struct KernelArgs {
 	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
 	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
 	int32_t _padt;
+	/* highest_valid_cost_ with the reference's early-exit semantics (hv_early_exit_kernel): per candidate and MapGrid critic g,
+	 * the weighted partial sum of the critics BEFORE g (what SimpleScoredSamplingPlanner::scoreTrajectory compares with the best
+	 * so far; -1 if scoring cannot reach g: generator rejected the sample, an earlier critic was negative, or g has scale 0) and
+	 * the largest valid cell value g looked up along the trajectory. Sweep launches only; null: not recorded. */
+	double* hv_pre;                  /* [n_scenes][n_candidates][4] */
+	float* hv_val;                   /* [n_scenes][n_candidates][4] */
 };
 
 #endif

@@ -863,6 +863,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 		// ---- the weighted total (SimpleScoredSamplingPlanner) -------------------------------------------
 		double total = -1.0;
 		int n_eval_grids = 0;  // MapGrid critics actually evaluated (for highest_valid_cost_)
+		double hv_pre[HMP_NUM_MAPGRIDS] = {-1.0, -1.0, -1.0, -1.0};   // -1: scoring does not reach the critic
 		if (active && !rejected) {
 			n_generated++;
 			double raw[HMP_NUM_COSTS];
@@ -898,7 +899,10 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			for (int k = 0; k < HMP_NUM_COSTS; ++k) {
 				double sc = P.scale[k];
 				if (sc == 0.0 || aborted) continue;
-				if (k >= HMP_COST_PATH && k <= HMP_COST_GOAL_FRONT) n_eval_grids |= 1 << (k - HMP_COST_PATH);
+				if (k >= HMP_COST_PATH && k <= HMP_COST_GOAL_FRONT) {
+					n_eval_grids |= 1 << (k - HMP_COST_PATH);
+					hv_pre[k - HMP_COST_PATH] = total;   // partial sum scoreTrajectory holds when it reaches this critic
+				}
 				double cst = raw[k];
 				if (cst < 0.0) {
 					total = cst;
@@ -924,6 +928,12 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			if (lane == 0 && hvb) atomicMax(&s_hv[g], hvb);
 		}
 		if (active && A.totals) A.totals[(size_t)scene * P.n_candidates + cand] = total;
+		if (active && A.hv_pre) {
+			const size_t o = ((size_t)scene * P.n_candidates + cand) * HMP_NUM_MAPGRIDS;
+			reinterpret_cast<double2*>(A.hv_pre + o)[0] = make_double2(hv_pre[0], hv_pre[1]);
+			reinterpret_cast<double2*>(A.hv_pre + o)[1] = make_double2(hv_pre[2], hv_pre[3]);
+			*reinterpret_cast<float4*>(A.hv_val + o) = make_float4(mg_hv[0], mg_hv[1], mg_hv[2], mg_hv[3]);
+		}
 	}
 
 	// ---- selection: thread -> warp -> block argmin -> last block merges (strict '<', lowest index wins ties) ----

@@ -69,6 +69,9 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
     gi = 0
     state = "init"
     log = ReplayLog()
+    # highest_valid_cost_ of the MapGrid critics: prepare() of cycle k + 1 moves cycle k's value into highest_valid_cost_prev_
+    # (src/map_grid_cost_function.cpp:76-77), which the unreachable-cell heuristic returns (:135-138)
+    hv_prev = [0.0, 0.0, 0.0, 0.0]
     for cyc in range(n_cycles):
         gx, gy, gyaw = goals[gi]
         dist = math.hypot(gx - x, gy - y)
@@ -126,15 +129,15 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
             planner.set_costmap(base.cells, base.origin_x, base.origin_y, base.resolution)
             grids = None
             if device_mapgrids:
-                planner.compute_mapgrid(0, plan, False)
-                planner.compute_mapgrid(1, plan, True)
-                planner.compute_mapgrid(2, plan, False)
-                planner.compute_mapgrid(3, front, True)
+                planner.compute_mapgrid(0, plan, False, hv_prev[0])
+                planner.compute_mapgrid(1, plan, True, hv_prev[1])
+                planner.compute_mapgrid(2, plan, False, hv_prev[2])
+                planner.compute_mapgrid(3, front, True, hv_prev[3])
             else:
                 grids = [scenes.mapgrid_wavefront(base.cells, base.origin_x, base.origin_y, base.resolution, pl_, lg_)
                          for pl_, lg_ in ((plan, False), (plan, True), (plan, False), (front, True))]
                 for g in range(4):
-                    planner.set_mapgrid(g, grids[g])
+                    planner.set_mapgrid(g, grids[g], hv_prev[g])
             planner.set_footprint(base.footprint)
             res, _ = planner.plan(w, smp, want_poses=False)
             log.plan_ms.append(1e3 * (time.perf_counter() - t0))
@@ -153,10 +156,11 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
                     grids = [planner.get_mapgrid(g, base.cells.shape) for g in range(4)]
                 from .capi import Scene
                 sc = Scene(w, oa, pa, None, base.cells, base.origin_x, base.origin_y, base.resolution, grids, base.footprint,
-                           (0.0, 0.0, 0.0, 0.0))
+                           tuple(hv_prev))
                 log.parity_checked += 1
                 if not on_plan(params, sc, smp, res):
                     log.parity_mismatch += 1
+            hv_prev = [float(v) for v in res.highest_valid_cost]
         elif state in ("init", "adjust"):
             err = head_err if state == "init" else _wrap(gyaw - th)
             want = math.copysign(min(max(abs(err), L.min_vel_theta), L.max_vel_theta), err)

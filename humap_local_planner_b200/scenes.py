@@ -340,4 +340,11 @@ def make_env_params(closest=(-1, -1, -1), robot_model: int = 1):
     e.person_containment_rate = 0.667
     e.obstacles_force_dynamic = 0
     e.people_force_dynamic = 1
+    # geometry of the non-circular footprint models (robot frame): two circles, a line, a 0.7 m x 0.5 m box with a nose
+    e.two_circles[:] = [0.2, 0.25, -0.2, 0.3]
+    e.line_xy[:] = [-0.3, 0.0, 0.3, 0.0]
+    poly = [(0.35, 0.15), (0.45, 0.0), (0.35, -0.15), (-0.35, -0.25), (-0.35, 0.25)]
+    e.n_polygon = len(poly)
+    for i, (px, py) in enumerate(poly):
+        e.polygon_xy[2 * i], e.polygon_xy[2 * i + 1] = px, py
     return e

@@ -263,8 +263,16 @@ typedef struct HmpShape {
 	double radius;                /* circle                                                           */
 	double vx, vy;                /* getCentroidVelocity()                                            */
 } HmpShape;
+#define HMP_MAX_ENV_POLYGON 16       /* vertices of a PolygonRobotFootprint */
+enum HmpRobotModel {
+	HMP_ROBOT_POINT = 0,          /* PointRobotFootprint, robot_footprint_model.h:55-95        */
+	HMP_ROBOT_CIRCULAR = 1,       /* CircularRobotFootprint, :98-140                           */
+	HMP_ROBOT_TWO_CIRCLES = 2,    /* TwoCirclesRobotFootprint, :143-226                        */
+	HMP_ROBOT_LINE = 3,           /* LineRobotFootprint, :228-294                              */
+	HMP_ROBOT_POLYGON = 4         /* PolygonRobotFootprint, :296-346                           */
+};
 typedef struct HmpEnvParams {
-	int32_t robot_model;          /* 0 PointRobotFootprint, 1 CircularRobotFootprint (robot_footprint_model.h:55-140) */
+	int32_t robot_model;          /* HmpRobotModel */
 	int32_t obstacles_closest_num, people_closest_num, groups_closest_num;   /* GeneralParams, -1 = all   */
 	double robot_radius;          /* getInscribedRadius()                                             */
 	double person_model_radius;   /* GeneralParams::person_model_radius                               */
@@ -273,6 +281,12 @@ typedef struct HmpEnvParams {
 	double person_containment_rate;          /* HumapPlanner::PERSON_POLYGON_CONTAINMENT_RATE = 0.667  */
 	int32_t obstacles_force_dynamic;         /* static_obj_interaction == INTERACTION_REPULSIVE_EVASIVE */
 	int32_t people_force_dynamic;            /* SfmParams::human_force_formulation_dynamic              */
+	/* footprint geometry of the non-circular models, robot frame (robot_radius stays getInscribedRadius() of the model) */
+	double two_circles[4];                   /* front_offset, front_radius, rear_offset, rear_radius    */
+	double line_xy[4];                       /* line_start (x, y), line_end (x, y)                      */
+	int32_t n_polygon;                       /* vertices of the polygon model, <= HMP_MAX_ENV_POLYGON   */
+	int32_t _pad;
+	double polygon_xy[2 * HMP_MAX_ENV_POLYGON];
 } HmpEnvParams;
 
 /* ---- result ------------------------------------------------------------------------------- */
@@ -439,7 +453,10 @@ int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid);
  * obstacle (enlarged) and of every kept person (a circle of person_model_radius). Output = the World::addObstacle call
  * sequence (obstacles first, then people) ready for HmpWorld.obstacles, plus the indices of the kept people / groups
  * (people_env_model_, groups_env_model_). *n_obstacles_out holds the capacity on entry. Ties of the N-closest metric are
- * resolved by input order (the reference's std::sort leaves them unspecified). Point and circular robot models only. */
+ * resolved by input order (the reference's std::sort leaves them unspecified). All five footprint models of
+ * robot_footprint_model.h (point, circular, two circles, line, polygon); their calculateClosestPoints are restated as written,
+ * including that the two-circle model returns the shortest VECTOR as the robot-side "pose" (:203-223) and that the polygon
+ * model measures against the footprint's robot-frame vertices (:340-344). */
 int hmp_build_environment(HmpContext* ctx, const HmpEnvParams* env, const double robot_pose[3], const double pose_ref[3],
                           const HmpShape* shapes, int32_t n_shapes, const double* vertices_xy, int32_t n_vertices,
                           const HmpPerson* people, int32_t n_people, const HmpGroup* groups, int32_t n_groups,

@@ -1743,10 +1743,181 @@ struct ShapeView {
 	}
 };
 
-// BaseRobotFootprintModel::calculateClosestPoints for the point and the circular model (robot_footprint_model.h:89-140)
-inline void calculateClosestPoints(const HmpEnvParams& env, const double pose[3], P2 obstacle_pt, Pose& robot_out, Pose& obstacle_out) {
+// ---- include/humap_local_planner/utils/vector_calculations.h (first-party) over teb_local_planner's
+// closest_point_on_line_segment_2d / check_line_segments_intersection_2d [RECALLED, parity unpinned] -------------------------
+inline double norm2(P2 v) { return std::sqrt(v.x * v.x + v.y * v.y); }
+inline P2 minus(P2 a, P2 b) { return {a.x - b.x, a.y - b.y}; }
+// v - v.normalized() * r (Eigen >= 3.3: normalized() returns a zero vector unchanged)
+inline P2 subtractRadius(P2 v, double r) {
+	double n2 = v.x * v.x + v.y * v.y;
+	if (!(n2 > 0.0)) return {v.x - v.x * r, v.y - v.y * r};
+	double n = std::sqrt(n2);
+	return {v.x - (v.x / n) * r, v.y - (v.y / n) * r};
+}
+inline P2 vectorPointToSegment(P2 point, P2 s, P2 e) { return minus(point, closestPointOnSegment(point, s, e)); }
+inline bool checkLineSegmentsIntersection(P2 a0, P2 a1, P2 b0, P2 b1) {
+	P2 line1 = minus(a1, a0), line2 = minus(b1, b0);
+	double denom = line1.x * line2.y - line2.x * line1.y;
+	if (denom == 0) return false;
+	bool denom_positive = denom > 0;
+	P2 aux = minus(a0, b0);
+	double s_numer = line1.x * aux.y - line1.y * aux.x;
+	if ((s_numer < 0) == denom_positive) return false;
+	double t_numer = line2.x * aux.y - line2.y * aux.x;
+	if ((t_numer < 0) == denom_positive) return false;
+	if (((s_numer > denom) == denom_positive) || ((t_numer > denom) == denom_positive)) return false;
+	return true;
+}
+// vector_calculations.h:33-63. Intersecting segments: the reference returns a default-constructed Eigen::Vector2d, i.e.
+// uninitialised memory; restated as the zero vector (deviation documented in DESIGN.md)
+inline P2 vectorSegmentToSegment(P2 l1s, P2 l1e, P2 l2s, P2 l2e) {
+	if (checkLineSegmentsIntersection(l1s, l1e, l2s, l2e)) return {0.0, 0.0};
+	P2 v[4] = {vectorPointToSegment(l1s, l2s, l2e), vectorPointToSegment(l1e, l2s, l2e), vectorPointToSegment(l2s, l1s, l1e),
+	           vectorPointToSegment(l2e, l1s, l1e)};
+	int idx = 0;
+	double shortest = norm2(v[0]);
+	for (int i = 1; i < 4; ++i) {
+		double len = norm2(v[i]);
+		if (len < shortest) {
+			shortest = len;
+			idx = i;
+		}
+	}
+	return v[idx];
+}
+inline P2 vectorPointToPolygon(P2 point, const std::vector<P2>& vertices) {   // :65-95
+	double dist = HUGE_VAL;
+	P2 vec{0.0, 0.0};
+	if (vertices.size() == 1) return minus(point, vertices.front());
+	for (int i = 0; i < (int)vertices.size() - 1; ++i) {
+		P2 nv = vectorPointToSegment(point, vertices[i], vertices[i + 1]);
+		double d = norm2(nv);
+		if (d < dist) {
+			dist = d;
+			vec = nv;
+		}
+	}
+	if (vertices.size() > 2) {
+		P2 nv = vectorPointToSegment(point, vertices.back(), vertices.front());
+		if (norm2(nv) < dist) return nv;
+	}
+	return vec;
+}
+inline P2 vectorSegmentToPolygon(P2 ls, P2 le, const std::vector<P2>& vertices) {   // :97-131
+	double dist = HUGE_VAL;
+	P2 vec{0.0, 0.0};
+	if (vertices.size() == 1) return vectorPointToSegment(vertices.front(), ls, le);
+	for (int i = 0; i < (int)vertices.size() - 1; ++i) {
+		P2 nv = vectorSegmentToSegment(ls, le, vertices[i], vertices[i + 1]);
+		double d = norm2(nv);
+		if (d < dist) {
+			dist = d;
+			vec = nv;
+		}
+	}
+	if (vertices.size() > 2) {
+		P2 nv = vectorSegmentToSegment(ls, le, vertices.back(), vertices.front());
+		double d = norm2(nv);
+		if (d < dist) {
+			dist = d;
+			vec = nv;
+		}
+	}
+	return vec;
+}
+inline P2 vectorPolygonToPolygon(const std::vector<P2>& v1, const std::vector<P2>& v2) {   // :133-165
+	double dist = HUGE_VAL;
+	P2 vec{0.0, 0.0};
+	if (v1.size() == 1) return vectorPointToPolygon(v1.front(), v2);
+	for (int i = 0; i < (int)v1.size() - 1; ++i) {
+		P2 nv = vectorSegmentToPolygon(v1[i], v1[i + 1], v2);
+		double d = norm2(nv);
+		if (d < dist) {
+			dist = d;
+			vec = nv;
+		}
+	}
+	if (v1.size() > 2) {
+		P2 nv = vectorSegmentToPolygon(v1.back(), v1.front(), v2);
+		double d = norm2(nv);
+		if (d < dist) {
+			dist = d;
+			vec = nv;
+		}
+	}
+	return vec;
+}
+inline std::vector<P2> shapeVertices(const ShapeView& sv) {
+	std::vector<P2> v;
+	for (int i = 0; i < sv.s->n_vertices; ++i) v.push_back(sv.vertex(i));
+	return v;
+}
+// Obstacle::getShortestVector(line_start, line_end), include/humap_local_planner/obstacles.h:98,167,235,298
+inline P2 shortestVectorToSegment(const ShapeView& sv, P2 ls, P2 le) {
+	const HmpShape* s = sv.s;
+	switch (s->type) {
+		case HMP_SHAPE_POINT: return vectorPointToSegment({s->x, s->y}, ls, le);
+		case HMP_SHAPE_CIRCLE: return subtractRadius(vectorPointToSegment({s->x, s->y}, ls, le), s->radius);
+		case HMP_SHAPE_LINE: return vectorSegmentToSegment({s->x, s->y}, {s->x2, s->y2}, ls, le);
+		default: return vectorSegmentToPolygon(ls, le, shapeVertices(sv));
+	}
+}
+// Obstacle::getShortestVector(polygon), obstacles.h:101,171,238,301
+inline P2 shortestVectorToPolygon(const ShapeView& sv, const std::vector<P2>& polygon) {
+	const HmpShape* s = sv.s;
+	switch (s->type) {
+		case HMP_SHAPE_POINT: return vectorPointToPolygon({s->x, s->y}, polygon);
+		case HMP_SHAPE_CIRCLE: return subtractRadius(vectorPointToPolygon({s->x, s->y}, polygon), s->radius);
+		case HMP_SHAPE_LINE: return vectorSegmentToPolygon({s->x, s->y}, {s->x2, s->y2}, polygon);
+		default: return vectorPolygonToPolygon(polygon, shapeVertices(sv));
+	}
+}
+
+// BaseRobotFootprintModel::calculateClosestPoints of the five footprint models (robot_footprint_model.h:89-95, :132-139,
+// :203-223, :279-291, :340-344), restated as written
+inline void calculateClosestPoints(const HmpEnvParams& env, const double pose[3], const ShapeView& sv, Pose& robot_out, Pose& obstacle_out) {
+	const P2 position{pose[0], pose[1]};
+	switch (env.robot_model) {
+		case HMP_ROBOT_TWO_CIRCLES: {
+			const double front_offset = env.two_circles[0], front_radius = env.two_circles[1], rear_offset = env.two_circles[2],
+			             rear_radius = env.two_circles[3];
+			const P2 dir{std::cos(pose[2]), std::sin(pose[2])};   // PoseSE2::orientationUnitVec
+			const P2 centre_front{position.x + front_offset * dir.x, position.y + front_offset * dir.y};
+			const P2 centre_rear{position.x + rear_offset * dir.x, position.y + rear_offset * dir.y};
+			const P2 obs_pt_front = sv.closestPoint(centre_front), obs_pt_rear = sv.closestPoint(centre_rear);
+			// "robot_pt_*" are vectors (v - v.normalized() * radius), and the shortest one becomes pts.robot
+			const P2 hyp[4] = {subtractRadius(minus(obs_pt_front, centre_front), front_radius), subtractRadius(minus(obs_pt_rear, centre_front), front_radius),
+			                   subtractRadius(minus(obs_pt_front, centre_rear), rear_radius), subtractRadius(minus(obs_pt_rear, centre_rear), rear_radius)};
+			const P2 obs[4] = {obs_pt_front, obs_pt_rear, obs_pt_front, obs_pt_rear};
+			int best = 0;
+			for (int k = 1; k < 4; ++k)
+				if (norm2(hyp[k]) < norm2(hyp[best])) best = k;   // std::sort by norm: insertion sort for 4 elements, first minimum first
+			obstacle_out = Pose(obs[best].x, obs[best].y, 0.0);
+			robot_out = Pose(hyp[best].x, hyp[best].y, pose[2]);
+			return;
+		}
+		case HMP_ROBOT_LINE: {
+			const double c = std::cos(pose[2]), s = std::sin(pose[2]);   // teb LineRobotFootprint::transformToWorld
+			const P2 ls{position.x + c * env.line_xy[0] - s * env.line_xy[1], position.y + s * env.line_xy[0] + c * env.line_xy[1]};
+			const P2 le{position.x + c * env.line_xy[2] - s * env.line_xy[3], position.y + s * env.line_xy[2] + c * env.line_xy[3]};
+			const P2 v = shortestVectorToSegment(sv, ls, le);
+			robot_out = Pose(pose[0], pose[1], pose[2]);
+			obstacle_out = Pose(position.x - v.x, position.y - v.y, 0.0);
+			return;
+		}
+		case HMP_ROBOT_POLYGON: {
+			std::vector<P2> vertices;   // vertices_ of the footprint: ROBOT frame, not transformed by the pose (as written, :340-344)
+			for (int i = 0; i < env.n_polygon; ++i) vertices.push_back({env.polygon_xy[2 * i], env.polygon_xy[2 * i + 1]});
+			const P2 v = shortestVectorToPolygon(sv, vertices);
+			robot_out = Pose(pose[0], pose[1], pose[2]);
+			obstacle_out = Pose(v.x, v.y, 0.0);
+			return;
+		}
+		default: break;
+	}
+	const P2 obstacle_pt = sv.closestPoint(position);
 	obstacle_out = Pose(obstacle_pt.x, obstacle_pt.y, 0.0);
-	if (env.robot_model == 0) {
+	if (env.robot_model == HMP_ROBOT_POINT) {
 		robot_out = Pose(pose[0], pose[1], pose[2]);
 		return;
 	}
@@ -1843,7 +2014,7 @@ EnvModel createEnvironmentModel(const HmpEnvParams& env, const double robot_pose
 		const HmpShape& sh = shapes[kept[k]];
 		ShapeView sv{&sh, verts};
 		Pose r, o;
-		calculateClosestPoints(env, pose_ref, sv.closestPoint({pose_ref[0], pose_ref[1]}), r, o);
+		calculateClosestPoints(env, pose_ref, sv, r, o);
 		enlargeObstacle(r, o, env.obstacle_extension_multiplier * env.robot_radius, 1.05 * env.ttc_collision_distance);
 		emit(r, o, sh.vx, sh.vy, 0.0, env.obstacles_force_dynamic != 0);
 	}
@@ -1857,7 +2028,7 @@ EnvModel createEnvironmentModel(const HmpEnvParams& env, const double robot_pose
 		circle.radius = env.person_model_radius;
 		ShapeView sv{&circle, nullptr};
 		Pose r, o;
-		calculateClosestPoints(env, pose_ref, sv.closestPoint({pose_ref[0], pose_ref[1]}), r, o);
+		calculateClosestPoints(env, pose_ref, sv, r, o);
 		emit(r, o, people[p].vx, people[p].vy, people[p].vth, env.people_force_dynamic != 0);
 	}
 	return m;

@@ -29,15 +29,17 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_c_layout():
     # sizes computed by the C compiler for include/hmp_planner.h (gcc, x86-64); a mismatch means the ctypes mirror drifted
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "hmp_planner.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "hmp_planner.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(HmpParams),sizeof(HmpWorld),sizeof(HmpObstacle),sizeof(HmpPerson),sizeof(HmpGroup),' \
-          'sizeof(HmpSampling),sizeof(HmpSample),sizeof(HmpResult),sizeof(HmpCosts));return 0;}\n'
+          'sizeof(HmpSampling),sizeof(HmpSample),sizeof(HmpResult),sizeof(HmpCosts),sizeof(HmpEnvParams),sizeof(HmpShape),' \
+          'sizeof(HmpEquisampled));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
     mine = [C.sizeof(t) for t in (capi.HmpParams, capi.HmpWorld, capi.HmpObstacle, capi.HmpPerson, capi.HmpGroup,
-                                  capi.HmpSampling, capi.HmpSample, capi.HmpResult, capi.HmpCosts)]
+                                  capi.HmpSampling, capi.HmpSample, capi.HmpResult, capi.HmpCosts, capi.HmpEnvParams, capi.HmpShape,
+                                  capi.HmpEquisampled)]
     assert mine == sizes
 
 

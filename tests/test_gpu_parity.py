@@ -572,8 +572,10 @@ def test_parameter_variants(planner, mutate, precise, layout):
     v = (g >= 0) & (o >= 0)
     if v.any():
         assert np.median(_rel_err(g[v], o[v])) < 1e-5
-    # highest_valid_cost_ of the four MapGrid critics (no early exit on either side)
-    ref = ob.plan(cy["params"], cy["sc"], cy["smp"], early_exit=False)["result"]
+    # highest_valid_cost_ of the MapGrid critics with the reference's semantics: only candidates the sequential, early-exiting
+    # scored-sampling loop hands to the critic count (src/map_grid_cost_function.cpp:76-77,87,135)
+    ref = ob.plan(cy["params"], cy["sc"], cy["smp"], early_exit=True, want=("totals",))["result"]
+    print(f"GATE hv precise={precise}: device {list(cy['res'].highest_valid_cost)} oracle(early exit) {list(ref.highest_valid_cost)}")
     assert np.allclose(np.array(cy["res"].highest_valid_cost), np.array(ref.highest_valid_cost))
 
 
@@ -689,10 +691,17 @@ def test_closed_loop_replay(planner, precise):
     from humap_local_planner_b200 import replay
     notes = []
 
+    hv_bad = []
+
     def check(params, sc, smp, res):
+        # the reference's own loop (early exit): winner and highest_valid_cost_ (which is next cycle's highest_valid_cost_prev_)
+        ee = ob.plan(params, sc, smp, early_exit=True, want=("totals",))["result"]
+        if precise and not np.allclose(np.array(res.highest_valid_cost)[2:], np.array(ee.highest_valid_cost)[2:]):
+            hv_bad.append((list(res.highest_valid_cost), list(ee.highest_valid_cost)))
         ref = ob.plan(params, sc, smp, early_exit=False, want=("totals",))
         tot = ref["totals"]
         rb = ref["result"].best_index
+        assert ee.best_index == rb
         if rb == res.best_index:
             return True
         # north_star: identical unless the reference's best totals are within 1e-4 relative of each other
@@ -703,17 +712,20 @@ def test_closed_loop_replay(planner, precise):
         return ok
 
     planner.set_precision(precise)
-    log = replay.run_replay(planner, n_cycles=900, on_plan=check, on_plan_every=25)
+    log = replay.run_replay(planner, n_cycles=900, on_plan=check, on_plan_every=(25 if not precise else 2))
     planner.set_precision(False)
     s = replay.summarize(log)
     # the state machine walks init -> move -> adjust -> stop and starts over with the next goal
     seq = s["state_sequence_head"]
     assert seq[:4] == ["init", "move", "adjust", "stop"] or seq[:3] == ["move", "adjust", "stop"], seq
     assert s["goals_reached"] >= 1 and s["move_cycles"] >= 50
-    assert s["parity_checked"] >= 5
+    assert s["parity_checked"] >= (5 if not precise else 200)
     if precise:
         # FP64 object loops (or FP32 sweep + FP64 refinement of the leaders): the device selection IS the oracle's selection
         assert s["parity_mismatch"] == 0, notes
+        # ... and highest_valid_cost_ of the customised MapGrid critics equals the early-exiting reference loop's on every
+        # checked plan (FP64 mode: exactly; refined mode: the FP32 partial sums of non-leaders decide borderline cases)
+        assert len(hv_bad) <= (0 if precise is True else max(1, s["parity_checked"] // 20)), hv_bad[:3]
     else:
         # FP32 sweep only (mode 0). Around a moving robot some candidates are chaotic: their rollouts oscillate with period
         # 2 near the stationary-robot threshold of World (speed <= 0.01 -> heading = yaw, world.cpp:26-30) and amplify a 1e-7
@@ -978,7 +990,11 @@ def _obstacle_table(arr, n):
 
 @pytest.mark.parametrize("seed,closest,model,pose_ref", [(0, (-1, -1, -1), 1, (0.0, 0.0, 0.0)), (1, (20, 3, 1), 1, (0.6, -0.3, 0.4)),
                                                         (2, (5, 0, -1), 0, (1.5, 1.0, -2.0)), (3, (0, 2, 0), 1, (-0.4, 0.8, 3.0)),
-                                                        (4, (12, -1, -1), 1, (2.0, 0.1, 0.0))])
+                                                        (4, (12, -1, -1), 1, (2.0, 0.1, 0.0)),
+                                                        # two-circle, line and polygon footprint models (robot_footprint_model.h:143-346)
+                                                        (5, (-1, -1, -1), 2, (0.3, 0.2, 0.7)), (6, (15, 4, 2), 2, (-0.5, 0.4, -2.4)),
+                                                        (7, (-1, -1, -1), 3, (0.2, -0.6, 1.1)), (8, (25, -1, -1), 3, (1.0, 0.5, -0.3)),
+                                                        (9, (-1, -1, -1), 4, (0.0, 0.0, 0.0)), (10, (18, 5, 1), 4, (0.7, -0.2, 2.0))])
 def test_environment_model(planner, seed, closest, model, pose_ref):
     cfg = scenes.CONFIGS["cfg1"]
     sc = scenes.make_scene(cfg, seed)
@@ -988,6 +1004,8 @@ def test_environment_model(planner, seed, closest, model, pose_ref):
     if seed == 4:
         env.obstacles_force_dynamic = 1
         env.obstacle_extension_multiplier = 3.0      # large extension: exercises the fallback stage of enlargeObstacle
+    if model >= 2:
+        env.obstacle_extension_multiplier = 0.5 if seed % 2 else 1.0
     robot_pose = (0.0, 0.0, 0.0)
     g_out, g_n, g_ps, g_gs = planner.build_environment(env, robot_pose, pose_ref, shapes, verts, sc._people, sc._groups)
     o_out, o_n, o_ps, o_gs = ob.build_environment(env, robot_pose, pose_ref, shapes, verts, sc._people, sc._groups)
@@ -997,7 +1015,12 @@ def test_environment_model(planner, seed, closest, model, pose_ref):
         assert len(shapes) - 12 + len(g_ps) <= g_n <= len(shapes) - 6 + len(g_ps)
     gt, ot = _obstacle_table(g_out, g_n), _obstacle_table(o_out, o_n)
     assert np.array_equal(gt[:, 9], ot[:, 9])
-    assert np.abs(gt - ot).max() < 1e-12
+    assert np.isfinite(ot).all() and np.abs(gt - ot).max() < 1e-12
+    if model >= 2:
+        # the models differ: the same scene through the circular model gives other closest points
+        env.robot_model = 1
+        c_out, c_n, _, _ = ob.build_environment(env, robot_pose, pose_ref, shapes, verts, sc._people, sc._groups)
+        assert c_n == o_n and np.abs(_obstacle_table(c_out, c_n) - ot).max() > 1e-3
 
 
 @pytest.mark.parametrize("seed,fis", [(0, True), (1, True), (2, False)])
@@ -1135,18 +1158,18 @@ def test_thread_layout_large_costmap(planner, size, res):
 
 
 def test_refined_replay_equals_fp64_on_every_plan(planner):
-    """Mode 2 against mode 1 (FP64 sweep = the oracle's selection, test_closed_loop_replay[fp64]) on EVERY plan of the first
-    200 cycles of the closed-loop replay, not only on sampled ones. Around a moving robot a good candidate's FP32 total can
+    """Mode 2 against mode 1 (FP64 sweep = the oracle's selection, test_closed_loop_replay[fp64]) on EVERY plan of all
+    1000 cycles of the closed-loop replay, not only on sampled ones. Around a moving robot a good candidate's FP32 total can
     be off by a cell's worth of an integer-valued critic (2.8 % seen at plan 93: the true winner ranked second in FP32,
     outside the 2 % window); the minimum leader count and the second refinement round exist for these cases."""
     from humap_local_planner_b200 import replay
     logs = {}
     for mode in (1, 2):
         planner.set_precision(mode)
-        logs[mode] = replay.run_replay(planner, n_cycles=200)
+        logs[mode] = replay.run_replay(planner, n_cycles=1000)
     planner.set_precision(False)
     a, b = np.array(logs[1].best), np.array(logs[2].best)
-    assert len(a) == len(b) and len(a) >= 150
+    assert len(a) == len(b) and len(a) >= 600
     assert np.array_equal(a, b), np.where(a != b)[0][:5]
 
 
