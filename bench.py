@@ -232,10 +232,16 @@ def run_batched(args, rank, local_rank, world, barrier, steps, warmup, n_scenes)
     pl.set_costmap(first.cells, first.origin_x, first.origin_y, first.resolution)
     pl.set_footprint(first.footprint)
 
+    split_ms = []
+
     def full_batch():
         # per step, from host buffers: costmaps + plans in, wave fronts on the device, worlds in, per-scene results out
+        t0 = time.perf_counter()
         pl.compute_mapgrid_batch(cells, plans, local_goal)
-        return pl.plan_batch(worlds, None, None, sampling, hv_prev=hv)
+        t1 = time.perf_counter()
+        r = pl.plan_batch(worlds, None, None, sampling, hv_prev=hv)
+        split_ms.append((1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
+        return r
 
     res = full_batch()
     C = res[0].n_candidates
@@ -289,6 +295,8 @@ def run_batched(args, rank, local_rank, world, barrier, steps, warmup, n_scenes)
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "e2e": {"value": S * C / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(n_local * Cc.sizeof(capi.HmpResult)), "steps": n_e2e,
+                    "ms_mapgrids_then_plan_rank0": [round(statistics.mean(x[0] for x in split_ms[-n_e2e:]), 2),
+                                                    round(statistics.mean(x[1] for x in split_ms[-n_e2e:]), 2)],
                     "what": "hmp_compute_mapgrid_batch (costmaps + plans up, wave fronts on the device) + hmp_plan_batch (worlds up, results down), wall clock"},
             "gpu_launches": int(launches), "clocks": clocks,
             "scenes_with_valid_winner": int(sum(1 for b, _ in gathered if b >= 0)),

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libhmp_planner.so")
+LIB_CHECK = os.path.join(LIB_DIR, "libhmp_planner_check.so")   # -DHMP_BOUNDS_CHECK debug build (tests/test_gpu_bounds.py)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
@@ -30,11 +31,13 @@ def _stale(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, check: bool = False) -> str:
+    """check=True builds the bounds-checked debug variant (every scene-derived shared / global index asserted on the device)."""
     srcs = [os.path.join(CSRC, "hmp_kernels.cu"), os.path.join(CSRC, "hmp_api.cu")]
     deps = srcs + [os.path.join(CSRC, "hmp_device.h"), os.path.join(CSRC, "hmp_sweep_tpc.inl"), os.path.join(HERE, "..", "include", "hmp_planner.h")]
-    if force or _stale(LIB, deps):
+    target = LIB_CHECK if check else LIB
+    if force or _stale(target, deps):
         os.makedirs(LIB_DIR, exist_ok=True)
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-DHMP_BOUNDS_CHECK"] if check else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + srcs
         subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return target

@@ -150,6 +150,7 @@ ABI_SYMBOLS = (
     "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
     "hmp_set_sweep_layout", "hmp_last_sweep_mode", "hmp_last_num_leaders_round2",
     "hmp_compute_mapgrid_batch", "hmp_set_mapgrids_batch_f32", "hmp_last_num_scenes", "hmp_last_fallback_rounds",
+    "hmp_debug_sweep_candidate",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -511,6 +512,14 @@ class Planner:
         in4 = np.ascontiguousarray(in4, dtype=np.float64).reshape(-1, 4)
         out = np.zeros((in4.shape[0], 2))
         self._check(self._lib.hmp_debug_fis(self._ctx, _ptr(in4), in4.shape[0], _ptr(out)))
+        return out
+
+    def debug_sweep_candidate(self, candidate: int) -> np.ndarray:
+        """What the thread-per-candidate sweep computed for one candidate of the last plan: 14 raw critics, seed (x, w), last pose."""
+        out = np.zeros(19)
+        self._lib.hmp_debug_sweep_candidate.argtypes = [C.c_void_p, _i, C.c_void_p]
+        self._lib.hmp_debug_sweep_candidate.restype = C.c_int
+        self._check(self._lib.hmp_debug_sweep_candidate(self._ctx, int(candidate), _ptr(out)))
         return out
 
     def launch_count(self) -> int:

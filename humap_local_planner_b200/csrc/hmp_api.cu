@@ -48,6 +48,9 @@ extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int 
                                                       int min_leaders, int n_scenes, const int32_t* active, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_hv_early_exit(const double* totals, const double* hv_pre, const float* hv_val, int C,
                                                     unsigned int* hv_out, int n_scenes, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_collect_topk(const double* totals, int C, const double* best_out, int K, double round2_window,
+                                                   int32_t* leaders, int32_t* count, double* thr_out, int n_scenes, const int32_t* active,
+                                                   cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_reselect(const double* totals, int C, double* best_out, const int32_t* active, int n_scenes,
                                                cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
@@ -182,9 +185,11 @@ struct HmpContext {
 	int last_n_leaders = 0;
 	int last_n_leaders2 = 0;        // ... of the second round (single-scene plans)
 	int last_explain_n = 0, last_explain_T = 0;   // shape of the forces hmp_explain left in h_out (0: overwritten since)
+	int debug_cand = -1;            // hmp_debug_sweep_candidate
 	int last_fallback_rounds = 0;   // extra refinement rounds of the last plan because FP64 rejected every leader (mode 2)
 	int refine_min_leaders = 16;     // the best-ranked candidates are refined whatever the window (HMP_REFINE_MIN_LEADERS)
 	int refine_rounds = 2;           // HMP_REFINE_ROUNDS=1 in the environment: first round only (A/B)
+	int refine_window_only = 0;      // HMP_REFINE_WINDOW_ONLY=1: round 1 by the relative window (the r01 rule) instead of by rank (A/B)
 	HmpEquisampled equi{};           // second generator of the pool (hmp_set_equisampled); enabled = 0 after hmp_create
 	std::vector<double> last_equi;   // its velocity samples of the last plan ([n][3])
 	bool dilated_dirty = true;       // costmap cells, footprint or separation changed since the dilated map was built
@@ -737,6 +742,7 @@ HmpContext* hmp_create(int device_id) {
 	ctx->prune_obstacle = getenv("HMP_NO_PRUNE") ? 0 : 1;
 	if (const char* e = getenv("HMP_REFINE_MIN_LEADERS")) ctx->refine_min_leaders = std::max(1, std::min(256, atoi(e)));
 	if (const char* e = getenv("HMP_REFINE_ROUNDS")) ctx->refine_rounds = std::max(1, std::min(2, atoi(e)));
+	if (getenv("HMP_REFINE_WINDOW_ONLY")) ctx->refine_window_only = 1;
 	if (const char* e = getenv("HMP_SWEEP_LAYOUT")) ctx->sweep_layout = std::max(0, std::min(2, atoi(e)));
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
@@ -1150,6 +1156,13 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	A.no_prune = ctx->prune_obstacle ? 0 : 1;
 	A.hv_pre = (double*)ctx->d_hvrec.p;
 	A.hv_val = (float*)((double*)ctx->d_hvrec.p + hv_items);
+	A.debug_cand = -1;
+	if (ctx->debug_cand >= 0) {   // hmp_debug_sweep_candidate: the thread-per-candidate sweep writes this candidate's raw critics
+		if ((rc = ctx->d_dbg.ensure(32 * sizeof(double)))) return rc;
+		CU(cudaMemsetAsync(ctx->d_dbg.p, 0xff, 32 * sizeof(double), ctx->stream));
+		A.debug_cand = ctx->debug_cand;
+		A.d_costs = (double*)ctx->d_dbg.p;
+	}
 
 	CU(cudaEventRecord(ctx->ev0, st));
 	// dilated max-cost map for the exact pruning of the obstacle critic (rebuilt when costmap / footprint / separation change)
@@ -1189,6 +1202,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	CU(cudaMemcpyAsync((unsigned char*)ctx->h_out.p + det_bytes, ctrl, cl.total, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 
+	A.d_costs = nullptr;
 	KernelArgs B = A;
 	B.hv_pre = nullptr;   // detail / refinement launches do not record (the sweep's records stand)
 	B.hv_val = nullptr;
@@ -1210,8 +1224,12 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		ctx->last_n_leaders = 0;
 	} else {
 		// selection refinement: leaders of the FP32 sweep -> FP64 rollouts -> winner among the refined totals
-		const int K = (NS == 1) ? (ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : ctx->sm_count)
-		                        : std::min(ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : 256, 32);
+		// Leaders per scene. Single-scene plans: the K best-ranked candidates, K = one wave of warp-per-candidate FP64 rollouts
+		// (8 per SM: 1184 on a B200; a wave costs the latency of ONE FP64 rollout whatever its size) -- or every candidate when
+		// the pool is smaller, in which case the plan is simply the FP64 result. Batches: the 32 best-ranked per scene.
+		const int k_cap = (NS == 1) ? (ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : ctx->sm_count * HMP_WARPS_PER_BLOCK)
+		                            : std::min(ctx->refine_max_leaders > 0 ? ctx->refine_max_leaders : 32, 256);
+		const int K = std::max(8, (std::min(k_cap, C) + 7) / 8 * 8);
 		const bool want_poses = (NS == 1);
 		const size_t nk = (size_t)NS * K;
 		const size_t r_doubles = nk * (HMP_NUM_COSTS + 3 + 1) + (want_poses ? nk * T * 3 : 0);
@@ -1230,8 +1248,13 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			int32_t* r_leaders = (int32_t*)((double*)base + r_doubles);
 			int32_t* r_nposes = r_leaders + nk;
 			int32_t* r_count = r_nposes + nk;
-			CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
-			                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, active, st));
+			// round 1: rank-based (the K lowest FP32 totals); round 2: everything not yet refined whose FP32 total lies within the
+			// window above the REFINED best (at most K, the lowest first)
+			if (round == 0 && !ctx->refine_window_only)
+				CU(hmp_dev_launch_collect_topk(A.totals, C, A.best_out, K, ctx->refine_window, r_leaders, r_count, r_thr, NS, active, st));
+			else
+				CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
+				                                  round ? r_thr : nullptr, round ? nullptr : r_thr, ctx->refine_min_leaders, NS, active, st));
 			KernelArgs Rf = A;
 			Rf.hv_pre = nullptr;
 			Rf.hv_val = nullptr;
@@ -1252,11 +1275,13 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			// instance any number up to 2 x sm_count in ~1.4 ms; the count is only known on the device, so the choice follows
 			// the previous cycle's count (consecutive control cycles have similar leader sets). The second round's list is
 			// almost always empty (its blocks find no candidate and leave): one warp per candidate, two per block.
-			if (NS == 1 && round == 0 && ctx->last_n_leaders <= ctx->sm_count) {
-				CU(hmp_dev_launch_plan(&Rf, std::min(K, ctx->sm_count), 3, smem, st));
+			if (NS == 1 && round == 0 && K <= ctx->sm_count) {
+				CU(hmp_dev_launch_plan(&Rf, K, 3, smem, st));   // a small pool: one block-cooperative FP64 rollout per SM
 			} else if (NS == 1) {
-				Rf.warps_per_ticket = 2;
-				CU(hmp_dev_launch_plan(&Rf, (K + 1) / 2, 1, smem, st));
+				// one wave: every SM takes ceil(K / SMs) candidates, one per warp (round 2 is almost always empty: its blocks leave)
+				const int wpt = std::max(1, std::min(HMP_WARPS_PER_BLOCK, (K + ctx->sm_count - 1) / ctx->sm_count));
+				Rf.warps_per_ticket = wpt;
+				CU(hmp_dev_launch_plan(&Rf, (K + wpt - 1) / wpt, 1, smem, st));
 			} else {
 				Rf.warps_per_ticket = HMP_WARPS_PER_BLOCK;
 				CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
@@ -2312,6 +2337,23 @@ int hmp_set_refinement(HmpContext* ctx, double rel_window, int32_t max_leaders) 
 int hmp_last_num_leaders(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders : -1; }
 
 int hmp_last_num_leaders_round2(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_leaders2 : -1; }
+
+// Parity hook: re-runs the last plan and returns what the thread-per-candidate SWEEP computed for one social candidate: the 14
+// raw critic values, the seed twist (x, w) and the pose after the last step (the detail / explain passes always run one warp
+// per candidate, so they cannot show a deviation of the sweep's own arithmetic). out19: 19 doubles (NaN: sweep ran another layout).
+int hmp_debug_sweep_candidate(HmpContext* ctx, int32_t candidate, double* out19) {
+	if (!ctx || !out19 || !ctx->last_valid || candidate < 0 || candidate >= ctx->last_dev_params.n_social) {
+		set_err("bad arguments or no previous plan");
+		return HMP_E_INVALID;
+	}
+	std::vector<HmpResult> res((size_t)ctx->last_n_scenes);
+	ctx->debug_cand = candidate;
+	int rc = hmp_replan_resident(ctx, res.data(), ctx->last_n_scenes);
+	ctx->debug_cand = -1;
+	if (rc) return rc;
+	CU(cudaMemcpy(out19, ctx->d_dbg.p, 19 * sizeof(double), cudaMemcpyDeviceToHost));
+	return HMP_OK;
+}
 
 int hmp_last_fallback_rounds(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_fallback_rounds : -1; }
 

@@ -197,7 +197,8 @@ struct KernelArgs {
 	int32_t _padf2;
 	int32_t warps_per_ticket;        /* candidates a block takes per ticket (1..HMP_WARPS_PER_BLOCK, 0 = all): the refinement
 	                                    pass spreads few candidates over many SMs to cut the latency of a rollout       */
-	int32_t _padt;
+	int32_t debug_cand;              /* thread-per-candidate sweep, parity hook: when d_costs is set, the raw critic values [14], the
+	                                    seed twist (x, w) and the last pose (x, y, yaw) of this candidate are written there [19]      */
 	/* highest_valid_cost_ with the reference's early-exit semantics (hv_early_exit_kernel): per candidate and MapGrid critic g,
 	 * the weighted partial sum of the critics BEFORE g (what SimpleScoredSamplingPlanner::scoreTrajectory compares with the best
 	 * so far; -1 if scoring cannot reach g: generator rejected the sample, an earlier critic was negative, or g has scale 0) and

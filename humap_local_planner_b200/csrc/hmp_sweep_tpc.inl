@@ -183,6 +183,17 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 	const DevParams& P = *reinterpret_cast<const DevParams*>(smem + L.off_params);
 	const unsigned char* blob = smem + L.off_scene;
 	const DevScene& S = *reinterpret_cast<const DevScene*>(blob);
+	HMP_CHECK(blockDim.x <= HMP_TPC_THREADS && (blockDim.x & 31) == 0, "block size of the thread-per-candidate sweep");
+	HMP_CHECK(S.blob_bytes <= A.scene_stride && S.off_static >= sizeof(DevScene) &&
+	              S.off_static + (size_t)max(S.n_static, S.n_static0) * sizeof(DevStatic) <= S.off_dynamic &&
+	              S.off_dynamic + (size_t)max(S.n_dynamic, S.n_dynamic_later) * sizeof(DevDynamic) <= S.off_people &&
+	              S.off_people + (size_t)S.n_people * sizeof(DevPerson) <= S.off_groups &&
+	              S.off_groups + (size_t)S.n_groups * sizeof(DevGroup) <= S.blob_bytes,
+	          "scene blob: record arrays overlap or leave the blob");
+	HMP_CHECK(!A.costmap_in_smem || (size_t)P.size_x * P.size_y <= A.costmap_stride, "costmap window larger than its staged stride");
+	// the packed copy of the static objects (16 bytes per object, pairs of 32) sits behind the staged layout
+	HMP_CHECK(((L.total + 15u) & ~15u) + (HMP_TPC_PACKED ? (uint32_t)((max(S.n_static0, S.n_static) + 1) / 2) * 32u : 0u) <= dynamic_smem_size(),
+	          "staging layout + packed static objects exceed the dynamic shared memory of the launch");
 	const DevStatic* statics = reinterpret_cast<const DevStatic*>(blob + S.off_static);
 	const DevDynamic* dynamics = reinterpret_cast<const DevDynamic*>(blob + S.off_dynamic);
 	const DevPerson* people = reinterpret_cast<const DevPerson*>(blob + S.off_people);
@@ -311,6 +322,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				for (int a = HMP_NUM_AMPLIFIERS - 1; a >= 0; --a) {
 					int n = P.amp_n[a];
 					int q = rem / n;
+					HMP_CHECK(n >= 1 && n <= HMP_MAX_AMP_VALUES, "amplifier axis length");
 					amp[a] = __ldg(&A.amp_values[a * HMP_MAX_AMP_VALUES + (rem - q * n)]);
 					rem = q;
 				}
@@ -657,6 +669,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				if (need && dil != nullptr) {
 					int mx, my;
 					if (world_to_map(G, x, y, mx, my)) {
+						HMP_CHECK((size_t)(my * G.sx + mx) < grid_cells, "dilated-map look-up outside the map");
 						const int dmax = (int)__ldg(&dil[my * G.sx + mx]);
 						// dmax < 254: no lethal / unknown cell in reach (see plan_kernel)
 						const bool skip = P.occdist_sum ? (dmax == 0) : (dmax <= ob_best && dmax < 254);
@@ -704,6 +717,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 						if (!world_to_map(G, px, py, mx, my)) {
 							mg_codes |= 4 << (8 * g);
 						} else {
+							HMP_CHECK((size_t)my * P.size_x + mx < grid_cells, "MapGrid look-up outside the grid");
 							float v = __ldg(&mapgrids[(size_t)g * grid_cells + (size_t)my * P.size_x + mx]);
 							if (v != unreachable_costs || P.mg_kernel[g] <= 0) {
 								if (v != obstacle_costs) mg_hv[g] = fmaxf(mg_hv[g], v);
@@ -892,6 +906,10 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			raw[HMP_COST_PERSONAL_SPACE] = (S.n_people > 0) ? (double)psi_max : 0.0;
 			raw[HMP_COST_FFORMATION] = (S.n_groups > 0) ? (double)fsi_max : 0.0;
 			raw[HMP_COST_PASSING_SPEED] = (S.n_people > 0) ? (double)ps_max : 0.0;
+			if (A.d_costs && cand == A.debug_cand) {   // parity hook (hmp_debug_sweep_candidate)
+				for (int k = 0; k < HMP_NUM_COSTS; ++k) A.d_costs[k] = raw[k];
+				A.d_costs[14] = seed_x; A.d_costs[15] = seed_w; A.d_costs[16] = x; A.d_costs[17] = y; A.d_costs[18] = th;
+			}
 
 			total = 0.0;
 			bool aborted = false;
@@ -927,6 +945,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			hvb = __reduce_max_sync(0xffffffffu, hvb);   // positive floats order like their bit patterns
 			if (lane == 0 && hvb) atomicMax(&s_hv[g], hvb);
 		}
+		HMP_CHECK(!active || (cand >= 0 && cand < P.n_candidates), "explored-totals index");
 		if (active && A.totals) A.totals[(size_t)scene * P.n_candidates + cand] = total;
 		if (active && A.hv_pre) {
 			const size_t o = ((size_t)scene * P.n_candidates + cand) * HMP_NUM_MAPGRIDS;
@@ -971,6 +990,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			}
 		}
 		unsigned long long* bb = A.block_best + ((size_t)scene * gridDim.x + blockIdx.x) * 2;
+		HMP_CHECK(bi < P.n_candidates, "block argmin index");
 		bb[0] = (bi >= 0) ? cost_key(b) : ~0ull;
 		bb[1] = (unsigned long long)(long long)bi;
 		atomicAdd(&counters[2], s_cnt[0]);

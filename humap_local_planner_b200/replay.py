@@ -194,6 +194,43 @@ def summarize(log: ReplayLog) -> dict:
             "recoveries": log.recoveries}
 
 
+def bench_line(args, rank, local_rank, world, barrier) -> Optional[dict]:
+    """`bench.py --cfg cfg4`: BASELINE config 5 -- consecutive 20 Hz planning cycles with moving people and the
+    init -> move -> adjust -> stop sequence; p50 / p99 latency of the full C-ABI cycle (costmap upload, four device wave
+    fronts, footprint, plan in the configured precision mode, result read back) for the stock sampling (72 candidates) and
+    for the 64k-candidate grid. --steps = cycles per run (default 40 -> 1000). One process per GPU runs the same replay."""
+    cycles = 1000 if args.steps == 40 else max(50, args.steps)
+    pl = Planner(local_rank)
+    pl.set_precision(int(args.precise))
+    pl.set_sweep_layout(int(args.layout))
+    run_replay(pl, n_cycles=60)   # warm-up (allocations, module load)
+    barrier()
+    l0 = pl.launch_count()
+    small = summarize(run_replay(pl, cycles))
+    big = summarize(run_replay(pl, cycles, sampling_axes=config.SAMPLING_64K))
+    launches = pl.launch_count() - l0
+    barrier()
+    pl.close()
+    if rank != 0:
+        return None
+    return {
+        "metric": "p50 planning-cycle latency at 64k candidates (closed-loop replay)", "value": big["p50_cycle_ms"], "unit": "ms",
+        "n_gpus": world, "steps": cycles, "warmup": 60, "ms_per_step": big["p50_cycle_ms"], "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": {0: "f32", 1: "f64", 2: "f32 sweep + f64 refinement of the leaders"}[int(args.precise)],
+        "data": "synthetic",
+        "config": {"workload": f"closed-loop replay (BASELINE config 5): {cycles} consecutive 20 Hz cycles, cfg0 world (4 moving people, 30 obstacle "
+                               "points), states init -> move -> adjust -> stop, full C-ABI cycle per MOVE cycle",
+                   "timing": "wall clock of the C-ABI calls of one cycle (host buffers in, result out)"},
+        "p50_cycle_ms_64k": big["p50_cycle_ms"], "p99_cycle_ms_64k": big["p99_cycle_ms"], "p50_gpu_ms_64k": big["p50_gpu_ms"],
+        "p99_gpu_ms_64k": big["p99_gpu_ms"], "move_cycles_64k": big["move_cycles"], "goals_reached_64k": big["goals_reached"],
+        "p50_cycle_ms_cfg0": small["p50_cycle_ms"], "p99_cycle_ms_cfg0": small["p99_cycle_ms"], "p50_gpu_ms_cfg0": small["p50_gpu_ms"],
+        "p99_gpu_ms_cfg0": small["p99_gpu_ms"], "move_cycles_cfg0": small["move_cycles"], "goals_reached_cfg0": small["goals_reached"],
+        "state_sequence_head": small["state_sequence_head"],
+        "e2e": {"value": big["p50_cycle_ms"], "unit": "ms", "h2d_bytes_per_step": 40000 + 4 * 400 + 4096, "d2h_bytes_per_step": 1416},
+        "gpu_launches": int(launches),
+    }
+
+
 if __name__ == "__main__":
     import argparse
     import json

@@ -488,6 +488,11 @@ int hmp_debug_last_forces(HmpContext* ctx, int32_t n, double* forces_out);
 /* FP32 FFMA throughput of the device measured with independent FMA chains at the main sweep's launch shape (TFLOP/s): the
  * measured denominator of the roofline fraction bench.py reports beside the nominal one. */
 int hmp_debug_measure_fp32_peak(HmpContext* ctx, double* tflops_out);
+/* Re-runs the last single-scene plan and returns what the thread-per-candidate SWEEP itself computed for one social candidate:
+ * out19 = the 14 raw critic values, the seed twist (x, w) and the pose after the last step (x, y, yaw); all NaN if the sweep
+ * ran in the warp-per-candidate layout. hmp_explain always runs one warp per candidate, so only this hook can show a deviation
+ * of the sweep's own arithmetic. */
+int hmp_debug_sweep_candidate(HmpContext* ctx, int32_t candidate, double* out19);
 /* Rollout steps of the last plan (SocialTrajectoryGenerator::computeStepsNumber), -1 if none. */
 int hmp_num_steps(HmpContext* ctx);
 

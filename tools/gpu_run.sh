@@ -35,6 +35,14 @@ if [[ "$WHAT" == *" prof "* ]]; then
   ncu --set full --clock-control none --import-source on -k regex:sweep_tpc -s 4 -c 1 -f -o $OUT/${TAG}_full $B > $OUT/ncu_full_$TAG.log 2>&1
   ls -la $OUT/${TAG}_full.ncu-rep
 fi
+if [[ "$WHAT" == *" hole "* ]]; then
+  python tools/selection_hole_stats.py --plans 120 > $OUT/selection_hole_$TAG.json 2> $OUT/selection_hole_$TAG.err
+  python -c "import json; print(json.load(open('$OUT/selection_hole_$TAG.json'))['summary'])" || tail -5 $OUT/selection_hole_$TAG.err
+fi
+if [[ "$WHAT" == *" replay "* ]]; then
+  python bench.py --cfg cfg4 > $OUT/bench_replay_$TAG.json 2> $OUT/bench_replay_$TAG.err
+  tail -c 900 $OUT/bench_replay_$TAG.json; echo
+fi
 if [[ "$WHAT" == *" prof1 "* ]]; then
   B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-cpu-baseline"
   ncu --set full --clock-control none --import-source on -k regex:plan_kernel -s 3 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
