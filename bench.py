@@ -215,7 +215,11 @@ def run_batched(args, rank, local_rank, world, barrier, steps, warmup, n_scenes)
         w.obstacles, w.people, w.groups = ob, pe, gr
         w.n_obstacles, w.n_people, w.n_groups = f["n_obstacles"], f["n_people"], f["n_groups"]
         keep.append((ob, pe, gr))
-    cells = np.stack([f["cells"] for f in flats])
+    # the per-cycle inputs live in page-locked memory (hmp_host_alloc), as a planner host would keep its staging buffers
+    cells_pin = capi.PinnedArray((n_local,) + flats[0]["cells"].shape, np.uint8)
+    cells = cells_pin.array
+    for k, f in enumerate(flats):
+        cells[k] = f["cells"]
     plans = []
     for g in range(4):
         xy = [f["plans"][g] for f in flats]

@@ -150,7 +150,7 @@ ABI_SYMBOLS = (
     "hmp_set_refinement", "hmp_last_num_leaders", "hmp_set_equisampled", "hmp_compute_cost_cloud", "hmp_build_environment", "hmp_compute_force_grid", "hmp_debug_measure_fp32_peak",
     "hmp_set_sweep_layout", "hmp_last_sweep_mode", "hmp_last_num_leaders_round2",
     "hmp_compute_mapgrid_batch", "hmp_set_mapgrids_batch_f32", "hmp_last_num_scenes", "hmp_last_fallback_rounds",
-    "hmp_debug_sweep_candidate",
+    "hmp_debug_sweep_candidate", "hmp_host_alloc", "hmp_host_free",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -237,6 +237,34 @@ def load_library() -> C.CDLL:
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (hmp_host_alloc); keep the object alive as long as the array is used."""
+
+    def __init__(self, shape, dtype):
+        lib = load_library()
+        lib.hmp_host_alloc.restype = C.c_void_p
+        lib.hmp_host_alloc.argtypes = [C.c_size_t]
+        lib.hmp_host_free.restype = None
+        lib.hmp_host_free.argtypes = [C.c_void_p]
+        self._lib = lib
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        self._ptr = lib.hmp_host_alloc(n)
+        if not self._ptr:
+            raise MemoryError(lib.hmp_last_error().decode())
+        buf = (C.c_char * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                self.array = None
+                self._lib.hmp_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
 
 
 class HmpError(RuntimeError):

@@ -177,6 +177,7 @@ struct HmpContext {
 	std::vector<uint8_t> h_cells;   // host copy of the single-scene costmap (scene 0 after a batch): seed test of the device wave front
 	int costmap_scenes = 0;         // scenes whose costmap is resident in d_costmaps (1 after hmp_set_costmap, n after a batch upload)
 	int batch_grid_scenes = 0;      // scenes whose four MapGrids are resident in d_mapgrids from a batch call (0: single-scene slots only)
+	int batch_wf_pending = 0;       // scenes of a hmp_compute_mapgrid_batch whose wave fronts still run on wf_stream[0] (0: none)
 	bool have_footprint = false;
 	int precise = 2;                 // 0 FP32, 1 FP64, 2 (default) FP32 sweep + FP64 refinement of the leaders
 	double refine_window = 0.02;     // leaders: FP32 total <= best * (1 + window)
@@ -817,6 +818,8 @@ int hmp_set_params(HmpContext* ctx, const HmpParams* params) {
 	return HMP_OK;
 }
 
+static int resolve_wavefronts(HmpContext* ctx);
+
 int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32_t size_y, double origin_x, double origin_y,
                     double resolution) {
 	if (!ctx || !cells || size_x <= 0 || size_y <= 0 || !(resolution > 0.0)) {
@@ -828,6 +831,10 @@ int hmp_set_costmap(HmpContext* ctx, const uint8_t* cells, int32_t size_x, int32
 		return HMP_E_CAPACITY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	if (ctx->batch_wf_pending) {   // a batch of wave fronts still reading the old cells must finish first
+		int rcw = resolve_wavefronts(ctx);
+		if (rcw) return rcw;
+	}
 	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g)   // a wave front still reading the old cells must finish first
 		if (ctx->wavefront_pending[g]) CU(cudaStreamSynchronize(ctx->wf_stream[g]));
 	if (size_x != ctx->size_x || size_y != ctx->size_y) {
@@ -871,6 +878,10 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	if (ctx->batch_wf_pending) {
+		int rcw = resolve_wavefronts(ctx);
+		if (rcw) return rcw;
+	}
 	if (ctx->wavefront_pending[grid]) {   // an uploaded grid replaces a device wave front still in flight for this slot
 		CU(cudaStreamSynchronize(ctx->wf_stream[grid]));
 		ctx->wavefront_pending[grid] = false;
@@ -912,6 +923,28 @@ int hmp_set_mapgrid(HmpContext* ctx, int32_t grid, const double* target_dist, do
 // Checks the overflow flag of queued wave fronts; a grid whose frontier overflowed the shared-memory queues is recomputed
 // with the scan kernel (never observed for 200 x 200 windows; kept for correctness on pathological maps).
 static int resolve_wavefronts(HmpContext* ctx) {
+	if (ctx->batch_wf_pending > 0) {
+		// batch of wave fronts (hmp_compute_mapgrid_batch): wait for the side stream, then redo any grid whose frontier queue
+		// overflowed with the scan-based kernel; h_seeds[0] = [status per (scene, grid)][seed offsets][seeds]
+		const int n_scenes = ctx->batch_wf_pending;
+		ctx->batch_wf_pending = 0;
+		CU(cudaEventSynchronize(ctx->wf_done[0]));
+		const size_t items = (size_t)n_scenes * HMP_NUM_MAPGRIDS;
+		const size_t n = (size_t)ctx->size_x * ctx->size_y;
+		const int* hs = (const int*)ctx->h_seeds[0].p;
+		const int* off = hs + items;
+		const int* d = (const int*)ctx->d_seeds[0].p;
+		bool any = false;
+		for (size_t it = 0; it < items; ++it) {
+			if (!hs[it]) continue;
+			const int s = (int)(it / HMP_NUM_MAPGRIDS);
+			CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p + (size_t)s * ctx->costmap_stride, ctx->size_x, ctx->size_y,
+			                            d + items + (items + 1) + off[it], off[it + 1] - off[it], (float*)ctx->d_mapgrids.p + it * n, ctx->stream));
+			ctx->launches++;
+			any = true;
+		}
+		if (any) CU(cudaStreamSynchronize(ctx->stream));
+	}
 	// join the side streams of the pending wave fronts, then read their overflow flags with ONE synchronisation
 	int status[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	bool any = false;
@@ -999,6 +1032,10 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
+	if (ctx->batch_wf_pending) {   // shares slot 0's staging buffers and side stream
+		int rcw = resolve_wavefronts(ctx);
+		if (rcw) return rcw;
+	}
 	const int sx = ctx->size_x, sy = ctx->size_y;
 	const size_t n = (size_t)sx * sy;
 	if (hmp_dev_wavefront_smem(sx, sy, 1) > ctx->max_smem_optin) {   // mark bits + both frontier queues
@@ -1568,22 +1605,18 @@ int hmp_compute_mapgrid_batch(HmpContext* ctx, int32_t n_scenes, const uint8_t* 
 	}
 	off[items] = (int)pos;
 	if ((rc = ctx->d_mapgrids.ensure(n * HMP_NUM_MAPGRIDS * sizeof(float) * n_scenes))) return rc;
-	cudaStream_t st = ctx->stream;
+	// The wave fronts run on a side stream and are NOT waited for here: the caller's next step (hmp_plan_batch packs and uploads
+	// the worlds) overlaps them; resolve_wavefronts() joins the stream and checks the overflow flags before the first kernel
+	// that reads the grids. The costmaps are on the device already (upload_batch_costmaps synchronised).
+	cudaStream_t st = ctx->wf_stream[0];
 	int* d = (int*)ctx->d_seeds[0].p;
 	CU(cudaMemcpyAsync(d, hs, words * sizeof(int), cudaMemcpyHostToDevice, st));
 	CU(hmp_dev_launch_wavefront_batch((const uint8_t*)ctx->d_costmaps.p, ctx->costmap_stride, sx, sy, d + items + (items + 1), d + items,
 	                                  (float*)ctx->d_mapgrids.p, d, n_scenes, st));
 	ctx->launches++;
-	CU(cudaMemcpyAsync(hs, d, items * sizeof(int), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	for (size_t it = 0; it < items; ++it) {
-		if (!hs[it]) continue;   // frontier queue overflowed: redo this grid with the scan-based kernel
-		const int s = (int)(it / HMP_NUM_MAPGRIDS);
-		CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p + (size_t)s * ctx->costmap_stride, sx, sy, d + items + (items + 1) + off[it],
-		                            off[it + 1] - off[it], (float*)ctx->d_mapgrids.p + it * n, st));
-		ctx->launches++;
-	}
-	CU(cudaStreamSynchronize(st));
+	CU(cudaMemcpyAsync(hs, d, items * sizeof(int), cudaMemcpyDeviceToHost, st));   // status words back into the pinned staging buffer
+	CU(cudaEventRecord(ctx->wf_done[0], st));
+	ctx->batch_wf_pending = n_scenes;
 	for (bool& b : ctx->have_grid) b = true;
 	ctx->batch_grid_scenes = n_scenes;
 	ctx->last_valid = false;
@@ -1628,7 +1661,6 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
-	if ((rc = resolve_wavefronts(ctx))) return rc;   // device wave fronts of single-scene calls still in flight
 	const size_t n = (size_t)ctx->size_x * ctx->size_y;
 	int T = -1;
 	size_t stride = 0;
@@ -1695,6 +1727,8 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 	}
 	CU(cudaMemcpyAsync(ctx->d_scenes.p, hs, stride * n_scenes, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	// device wave fronts still in flight (hmp_compute_mapgrid[_batch]) ran beside the packing above; join them now
+	if ((rc = resolve_wavefronts(ctx))) return rc;
 	if (cells) {
 		if ((rc = upload_batch_costmaps(ctx, cells, n_scenes))) return rc;
 	}
@@ -2353,6 +2387,20 @@ int hmp_debug_sweep_candidate(HmpContext* ctx, int32_t candidate, double* out19)
 	if (rc) return rc;
 	CU(cudaMemcpy(out19, ctx->d_dbg.p, 19 * sizeof(double), cudaMemcpyDeviceToHost));
 	return HMP_OK;
+}
+
+// Page-locked host memory for the buffers a caller hands to the batch entry points every cycle (costmaps, plans, float
+// grids): copies from it run at the full PCIe rate and asynchronously; from pageable memory the driver stages them.
+void* hmp_host_alloc(size_t bytes) {
+	void* p = nullptr;
+	if (cudaMallocHost(&p, std::max<size_t>(bytes, 1)) != cudaSuccess) {
+		set_err("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+void hmp_host_free(void* p) {
+	if (p) cudaFreeHost(p);
 }
 
 int hmp_last_fallback_rounds(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_fallback_rounds : -1; }

@@ -31,6 +31,16 @@
 #ifndef HMP_MIN_BLOCKS
 #define HMP_MIN_BLOCKS 2
 #endif
+#ifndef HMP_F64_FAST
+#define HMP_F64_FAST 1   /* 1: FP64 object loops with rsqrt-based lengths and one merged exponential per static object (ulp-level
+                            differences from the literal form; cfg2 exact-mode sweep 56.0 -> 51.6 ms, r02d A/B); 0: the literal form */
+#endif
+#ifndef HMP_F64_STATIC_UNROLL
+#define HMP_F64_STATIC_UNROLL 2   /* static objects in flight per lane in the FP64 instances */
+#endif
+#ifndef HMP_F64_SWEEP_MIN_BLOCKS
+#define HMP_F64_SWEEP_MIN_BLOCKS 2   /* resident blocks per SM the FP64 sweep (precision mode 1) is register-budgeted for */
+#endif
 
 /* Rollout-invariant record of one object treated with the STATIC interaction formulation
  * (reference StaticObject, world.h:24-41). d0 = object point - robot-side point at t = 0; during the

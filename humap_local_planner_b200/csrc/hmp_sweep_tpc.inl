@@ -112,6 +112,65 @@ __device__ __noinline__ PeopleMax people_critics_generic(const DevPerson* people
 	return m;
 }
 
+#ifndef HMP_TPC_STATIC_CALL
+#define HMP_TPC_STATIC_CALL 0   /* 1: the packed static-object loop is an out-of-line function: the call boundary parks the caller's
+                                   per-candidate state (pose, critic accumulators, amplified parameters) on the stack, so that the
+                                   loop body has the whole register file and several pairs of objects in flight */
+#endif
+#ifndef HMP_TPC_CALL_UNROLL
+#define HMP_TPC_CALL_UNROLL 2
+#endif
+struct StaticSum {
+	float fx, fy, dmin, gmin;
+};
+// The packed static-object loop of sweep_tpc_kernel (same statements, see there), out of line.
+__device__ __noinline__ StaticSum static_loop_packed(const float4* __restrict__ pairs, int npairs, float rxh, float ryh, float rxl, float ryl,
+                                                     float yx, float yy, float yl2, float hx, float hy, float ih, float nbw_l2, float fovn_l2,
+                                                     float nawq) {
+	const float2 nrxh2 = bc2(-rxh), nryh2 = bc2(-ryh), nrxl2 = bc2(-rxl), nryl2 = bc2(-ryl);
+	const float2 yx2 = bc2(yx), yy2 = bc2(yy), nyl2_2 = bc2(-yl2);
+	const float2 hx2 = bc2(hx), hy2 = bc2(hy), nhx2 = bc2(-hx), ih2 = bc2(ih);
+	const float2 nbw2 = bc2(nbw_l2), fovn2 = bc2(fovn_l2), nawq2 = bc2(nawq);
+	const float2 NHALF2 = bc2(-0.5f), C15_2 = bc2(1.5f), HALF2 = bc2(0.5f);
+	float2 fsx2 = make_float2(0.f, 0.f), fsy2 = make_float2(0.f, 0.f);
+	float dminp = CUDART_INF_F, gmin = CUDART_INF_F;
+	constexpr int CALL_UNROLL = HMP_TPC_CALL_UNROLL;
+#pragma unroll CALL_UNROLL
+	for (int p = 0; p < npairs; ++p) {
+		const float4 a4 = pairs[2 * p], b4 = pairs[2 * p + 1];   // warp-uniform addresses: broadcast
+		const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(a4.x, a4.y), nrxh2), __fadd2_rn(make_float2(b4.x, b4.y), nrxl2));
+		const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(a4.z, a4.w), nryh2), __fadd2_rn(make_float2(b4.z, b4.w), nryl2));
+		const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+		const float2 bx = __fadd2_rn(dx, yx2), by = __fadd2_rn(dy, yy2);
+		const float2 b2 = __ffma2_rn(bx, bx, __fmul2_rn(by, by));
+		float2 ia = make_float2(rsqrt_ftz(d2.x), rsqrt_ftz(d2.y));
+		float2 ib = make_float2(rsqrt_ftz(b2.x), rsqrt_ftz(b2.y));
+		ia = __fmul2_rn(ia, __ffma2_rn(__fmul2_rn(__fmul2_rn(d2, NHALF2), ia), ia, C15_2));
+		ib = __fmul2_rn(ib, __ffma2_rn(__fmul2_rn(__fmul2_rn(b2, NHALF2), ib), ib, C15_2));
+		const float2 dist = __fmul2_rn(d2, ia), bl = __fmul2_rn(b2, ib);
+		const float2 sum = __fadd2_rn(dist, bl);
+		const float2 w2 = __ffma2_rn(sum, sum, nyl2_2);
+		float2 iw = make_float2(rsqrt_ftz(w2.x), rsqrt_ftz(w2.y));
+		iw = __fmul2_rn(iw, __ffma2_rn(__fmul2_rn(__fmul2_rn(w2, NHALF2), iw), iw, C15_2));
+		const float2 w = __fmul2_rn(__fmul2_rn(w2, iw), HALF2);
+		dminp = fminf(dminp, fminf(dist.x, dist.y));
+		gmin = fminf(gmin, fminf(fminf(fminf(d2.x, d2.y), fminf(b2.x, b2.y)), fminf(w2.x, w2.y)));
+		const float2 ex = __ffma2_rn(bx, ib, __fmul2_rn(dx, ia));
+		const float2 ey = __ffma2_rn(by, ib, __fmul2_rn(dy, ia));
+		const float2 dot = __ffma2_rn(dx, hx2, __fmul2_rn(dy, hy2));
+		const float2 crs = __ffma2_rn(dx, hy2, __fmul2_rn(dy, nhx2));
+		const float2 ihd = __fmul2_rn(ia, ih2);
+		const float2 cs2 = __fmul2_rn(dot, ihd), sn2 = __fmul2_rn(make_float2(fabsf(crs.x), fabsf(crs.y)), ihd);
+		const float2 ar = angle_from_cos_sin2(cs2, sn2);
+		const float2 expo = __ffma2_rn(w, nbw2, __fmul2_rn(__fmul2_rn(ar, ar), fovn2));
+		const float2 e = make_float2(ex2_ftz(expo.x), ex2_ftz(expo.y));
+		const float2 ng = __fmul2_rn(__fmul2_rn(nawq2, e), __fmul2_rn(sum, w));
+		fsx2 = __ffma2_rn(ng, ex, fsx2);
+		fsy2 = __ffma2_rn(ng, ey, fsy2);
+	}
+	return {fsx2.x + fsx2.y, fsy2.x + fsy2.y, dminp, gmin};
+}
+
 #ifndef HMP_TPC_DYN_UNROLL
 #define HMP_TPC_DYN_UNROLL 1
 #endif
@@ -444,6 +503,22 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 					if (P.fov_method == 0) {
 						int j0 = 0;
 #if HMP_TPC_PACKED
+#if HMP_TPC_STATIC_CALL
+						if (forces_on) {
+							const int npairs = ns >> 1;
+							const float rxh = (float)rxd, ryh = (float)ryd;
+							const bool moving = !(speed_d <= (SC)0.01);
+							const StaticSum ss = static_loop_packed(pairs, npairs, rxh, ryh, (float)(rxd - (double)rxh), (float)(ryd - (double)ryh), yx, yy,
+							                                        yl2, moving ? ux : c_r, moving ? uy : s_r, moving ? (SC)1 / speed_d : (SC)1, nbw_l2,
+							                                        fovn_l2, -0.25f * aw_g);
+							if (ss.gmin > 1e-10f) {
+								j0 = 2 * npairs;
+								fsx = ss.fx;
+								fsy = ss.fy;
+								dmin = fminf(dmin, ss.dmin);
+							}
+						}
+#else
 						if (forces_on) {
 							// ---- two objects per iteration in packed FP32x2 arithmetic; same formulas as static_body ----
 							const int npairs = ns >> 1;
@@ -504,6 +579,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 								dmin = fminf(dmin, dminp);
 							}
 						}
+#endif
 #endif
 #pragma unroll TPC_UNROLL
 						for (int j = j0; j < ns; ++j) static_body(std::true_type{}, j);

@@ -26,6 +26,7 @@
 #ifndef HMP_PLANNER_H_
 #define HMP_PLANNER_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -418,6 +419,11 @@ int hmp_compute_mapgrid_batch(HmpContext* ctx, int32_t n_scenes, const uint8_t* 
  * buffers, target_dist[g] + s * size_x * size_y = grid g of scene s; no conversion pass, full PCIe rate from pinned memory.
  * They stay resident for hmp_plan_batch(..., target_dist = NULL, ...). */
 int hmp_set_mapgrids_batch_f32(HmpContext* ctx, int32_t n_scenes, const float* const target_dist[HMP_NUM_MAPGRIDS]);
+
+/* Page-locked host memory for the buffers handed to the batch entry points every cycle (costmaps, plans, float grids): copies
+ * from it run asynchronously at the full PCIe rate (the driver stages copies from pageable memory). NULL on failure. */
+void* hmp_host_alloc(size_t bytes);
+void hmp_host_free(void* p);
 
 /* Re-runs the last hmp_plan / hmp_plan_batch on the scene data still resident in device memory (only
  * the few-KB parameter block is re-sent and the result read back). `results` must hold results_capacity >=
