@@ -39,8 +39,12 @@ extern "C" cudaError_t hmp_dev_launch_env_filter(const HmpShape* shapes, int n_s
                                                  double person_radius, double containment_rate, double rx, double ry, int32_t* keep,
                                                  double* metric, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_env_closest(const HmpShape* shapes, const double* verts, const HmpPerson* people, const int32_t* objects,
-                                                  int n_objects, const double* positions_xy, int n_positions, double yaw,
+                                                  const int32_t* counts, int row_stride, const double* positions_xy, int n_positions, double yaw,
                                                   const HmpEnvParams* env, HmpObstacle* out, cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_env_select(const int32_t* keep, const double* metric, int n_shapes, const HmpPerson* people, int n_people,
+                                                 const HmpGroup* groups, int n_groups, double rx, double ry, int n_obst_max, int n_people_max,
+                                                 int n_groups_max, double* scratch_metric, int32_t* objects_out, int32_t* people_out,
+                                                 int32_t* groups_out, int32_t* counts_out, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_dilate(const uint8_t* cm, int sx, int sy, uint32_t stride, float radius, uint8_t* out,
                                              int n_scenes, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_collect_leaders(const double* totals, int C, const double* best_out, double rel_window, int K,
@@ -2018,34 +2022,30 @@ int hmp_compute_cost_cloud(HmpContext* ctx, float* cloud6, uint8_t* valid) {
 // ---- environment model ---------------------------------------------------------------------------------------------
 namespace {
 
-// HumapPlanner::selectRelevant (humap_planner.h:387-427): everything in input order when N is negative ((size_t)-1) or not
-// smaller than the count, else the N smallest metrics (ties by input order)
-std::vector<int> select_relevant(const std::vector<double>& metric, int max_num) {
-	std::vector<int> idx(metric.size());
-	std::iota(idx.begin(), idx.end(), 0);
-	if (max_num < 0 || metric.size() <= (size_t)max_num) return idx;
-	if (max_num == 0) return {};
-	std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return metric[a] < metric[b]; });
-	idx.resize((size_t)max_num);
-	return idx;
-}
-
 struct EnvSelection {
-	std::vector<int32_t> objects;          // >= 0 shape index, < 0 person -(index + 1); World::addObstacle order
-	std::vector<int32_t> people, groups;   // people_env_model_, groups_env_model_
+	// host copies, valid after the caller's stream synchronisation (env_select queues their read-back)
+	std::vector<int32_t> objects;          // >= 0 shape index, < 0 person -(index + 1); World::addObstacle order (first counts[0] + counts[1])
+	std::vector<int32_t> people, groups;   // people_env_model_, groups_env_model_ (first counts[1] / counts[2] entries)
+	int32_t counts[3] = {0, 0, 0};         // selected shapes, people, groups
+	int row_stride = 0;                    // capacity of one position's row of closest-point records (shapes + people)
 	// device pointers into ctx->d_env (valid until the next call)
 	const HmpShape* d_shapes = nullptr;
 	const double* d_verts = nullptr;
 	const HmpPerson* d_people = nullptr;
 	int32_t* d_objects = nullptr;
+	int32_t* d_counts = nullptr;
+	int32_t* d_psel = nullptr;
+	int32_t* d_gsel = nullptr;
+	int n_people = 0, n_groups = 0;
 	double* d_positions = nullptr;
 	HmpObstacle* d_out = nullptr;
 };
 
 size_t align16(size_t v) { return (v + 15) / 16 * 16; }
 
-// uploads the inputs, filters + ranks the shapes on the device, selects on the host, uploads the object list and reserves
-// room for n_positions x objects closest-point records
+// Uploads the inputs, then on the device: extractNonPeopleObstacles + the N-closest metric (env_filter_kernel) and
+// selectRelevant for obstacles / people / groups (env_select_kernel). Nothing is waited for: the selection stays on the device
+// for env_closest_points_kernel, its read-back into `sel` is queued and becomes valid with the caller's synchronisation.
 int env_select(HmpContext* ctx, const HmpEnvParams& env, const double robot_pose[3], const HmpShape* shapes, int n_shapes,
                const double* verts, int n_verts, const HmpPerson* people, int n_people, const HmpGroup* groups, int n_groups,
                int n_positions, EnvSelection& sel) {
@@ -2065,64 +2065,90 @@ int env_select(HmpContext* ctx, const HmpEnvParams& env, const double robot_pose
 			return HMP_E_INVALID;
 		}
 	}
+	const size_t n_obj_max = (size_t)n_shapes + n_people;
 	const size_t b_shapes = align16(std::max(1, n_shapes) * sizeof(HmpShape));
 	const size_t b_verts = align16(std::max(1, n_verts) * 2 * sizeof(double));
 	const size_t b_people = align16(std::max(1, n_people) * sizeof(HmpPerson));
+	const size_t b_groups = align16(std::max(1, n_groups) * sizeof(HmpGroup));
 	const size_t b_keep = align16(std::max(1, n_shapes) * sizeof(int32_t));
 	const size_t b_metric = align16(std::max(1, n_shapes) * sizeof(double));
-	const size_t n_obj_max = (size_t)n_shapes + n_people;
+	const size_t b_scratch = align16(std::max(1, std::max(n_people, n_groups)) * sizeof(double));
 	const size_t b_objects = align16(std::max<size_t>(1, n_obj_max) * sizeof(int32_t));
+	const size_t b_psel = align16(std::max(1, n_people) * sizeof(int32_t));
+	const size_t b_gsel = align16(std::max(1, n_groups) * sizeof(int32_t));
+	const size_t b_counts = 16;
 	const size_t b_pos = align16(std::max(1, n_positions) * 2 * sizeof(double));
 	const size_t b_out = align16(std::max<size_t>(1, n_obj_max * n_positions) * sizeof(HmpObstacle));
 	int rc;
-	if ((rc = ctx->d_env.ensure(b_shapes + b_verts + b_people + b_keep + b_metric + b_objects + b_pos + b_out))) return rc;
-	unsigned char* base = (unsigned char*)ctx->d_env.p;
-	HmpShape* d_shapes = (HmpShape*)base;
-	double* d_verts = (double*)(base + b_shapes);
-	HmpPerson* d_people = (HmpPerson*)(base + b_shapes + b_verts);
-	int32_t* d_keep = (int32_t*)(base + b_shapes + b_verts + b_people);
-	double* d_metric = (double*)((unsigned char*)d_keep + b_keep);
-	sel.d_objects = (int32_t*)((unsigned char*)d_metric + b_metric);
-	sel.d_positions = (double*)((unsigned char*)sel.d_objects + b_objects);
-	sel.d_out = (HmpObstacle*)((unsigned char*)sel.d_positions + b_pos);
+	if ((rc = ctx->d_env.ensure(b_shapes + b_verts + b_people + b_groups + b_keep + b_metric + b_scratch + b_objects + b_psel + b_gsel + b_counts +
+	                            b_pos + b_out)))
+		return rc;
+	unsigned char* q = (unsigned char*)ctx->d_env.p;
+	auto take = [&](size_t bytes) {
+		unsigned char* r = q;
+		q += bytes;
+		return r;
+	};
+	HmpShape* d_shapes = (HmpShape*)take(b_shapes);
+	double* d_verts = (double*)take(b_verts);
+	HmpPerson* d_people = (HmpPerson*)take(b_people);
+	HmpGroup* d_groups = (HmpGroup*)take(b_groups);
+	int32_t* d_keep = (int32_t*)take(b_keep);
+	double* d_metric = (double*)take(b_metric);
+	double* d_scratch = (double*)take(b_scratch);
+	sel.d_objects = (int32_t*)take(b_objects);
+	int32_t* d_psel = (int32_t*)take(b_psel);
+	int32_t* d_gsel = (int32_t*)take(b_gsel);
+	sel.d_counts = (int32_t*)take(b_counts);
+	sel.d_positions = (double*)take(b_pos);
+	sel.d_out = (HmpObstacle*)take(b_out);
 	sel.d_shapes = d_shapes;
 	sel.d_verts = d_verts;
 	sel.d_people = d_people;
+	sel.row_stride = (int)n_obj_max;
 	cudaStream_t st = ctx->stream;
 	if (n_shapes > 0) CU(cudaMemcpyAsync(d_shapes, shapes, (size_t)n_shapes * sizeof(HmpShape), cudaMemcpyHostToDevice, st));
 	if (n_verts > 0) CU(cudaMemcpyAsync(d_verts, verts, (size_t)n_verts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
 	if (n_people > 0) CU(cudaMemcpyAsync(d_people, people, (size_t)n_people * sizeof(HmpPerson), cudaMemcpyHostToDevice, st));
-	std::vector<int32_t> keep((size_t)n_shapes);
-	std::vector<double> metric((size_t)n_shapes);
+	if (n_groups > 0) CU(cudaMemcpyAsync(d_groups, groups, (size_t)n_groups * sizeof(HmpGroup), cudaMemcpyHostToDevice, st));
 	if (n_shapes > 0) {
 		CU(hmp_dev_launch_env_filter(d_shapes, n_shapes, d_verts, d_people, n_people, env.person_model_radius, env.person_containment_rate,
 		                             robot_pose[0], robot_pose[1], d_keep, d_metric, st));
 		ctx->launches++;
-		CU(cudaMemcpyAsync(keep.data(), d_keep, (size_t)n_shapes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(metric.data(), d_metric, (size_t)n_shapes * sizeof(double), cudaMemcpyDeviceToHost, st));
 	}
+	CU(hmp_dev_launch_env_select(d_keep, d_metric, n_shapes, d_people, n_people, d_groups, n_groups, robot_pose[0], robot_pose[1],
+	                             env.obstacles_closest_num, env.people_closest_num, env.groups_closest_num, d_scratch, sel.d_objects, d_psel,
+	                             d_gsel, sel.d_counts, st));
+	ctx->launches++;
+	sel.d_psel = d_psel;
+	sel.d_gsel = d_gsel;
+	sel.n_people = n_people;
+	sel.n_groups = n_groups;
+	return HMP_OK;
+}
+
+// Reads the selection and n_positions rows of closest-point records back through the pinned staging buffer: ONE synchronisation.
+int env_read_back(HmpContext* ctx, EnvSelection& sel, int n_positions, std::vector<HmpObstacle>& records) {
+	const size_t cap = (size_t)sel.row_stride;
+	const size_t o_counts = 0, o_objects = 16, o_people = o_objects + align16(std::max<size_t>(1, cap) * 4);
+	const size_t o_groups = o_people + align16(std::max(1, sel.n_people) * 4), o_rec = o_groups + align16(std::max(1, sel.n_groups) * 4);
+	const size_t total = o_rec + std::max<size_t>(1, cap * n_positions) * sizeof(HmpObstacle);
+	int rc;
+	if ((rc = ctx->h_out.ensure(total))) return rc;
+	ctx->last_explain_n = 0;   // h_out is reused
+	unsigned char* h = (unsigned char*)ctx->h_out.p;
+	cudaStream_t st = ctx->stream;
+	CU(cudaMemcpyAsync(h + o_counts, sel.d_counts, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	if (cap > 0) CU(cudaMemcpyAsync(h + o_objects, sel.d_objects, cap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	if (sel.n_people > 0) CU(cudaMemcpyAsync(h + o_people, sel.d_psel, (size_t)sel.n_people * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	if (sel.n_groups > 0) CU(cudaMemcpyAsync(h + o_groups, sel.d_gsel, (size_t)sel.n_groups * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+	if (cap > 0) CU(cudaMemcpyAsync(h + o_rec, sel.d_out, cap * n_positions * sizeof(HmpObstacle), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	std::vector<int> kept;
-	std::vector<double> kept_metric;
-	for (int i = 0; i < n_shapes; ++i) {
-		if (keep[i]) {
-			kept.push_back(i);
-			kept_metric.push_back(metric[i]);
-		}
-	}
-	sel.objects.clear();
-	for (int k : select_relevant(kept_metric, env.obstacles_closest_num)) sel.objects.push_back(kept[k]);
-	std::vector<double> m;
-	for (int p = 0; p < n_people; ++p) m.push_back(std::hypot(people[p].x - robot_pose[0], people[p].y - robot_pose[1]));
-	sel.people.clear();
-	for (int p : select_relevant(m, env.people_closest_num)) sel.people.push_back(p);
-	m.clear();
-	for (int g = 0; g < n_groups; ++g) m.push_back(std::hypot(groups[g].x - robot_pose[0], groups[g].y - robot_pose[1]));
-	sel.groups.clear();
-	for (int g : select_relevant(m, env.groups_closest_num)) sel.groups.push_back(g);
-	for (int32_t p : sel.people) sel.objects.push_back(-(p + 1));
-	if (!sel.objects.empty())
-		CU(cudaMemcpyAsync(sel.d_objects, sel.objects.data(), sel.objects.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+	std::memcpy(sel.counts, h + o_counts, 3 * sizeof(int32_t));
+	sel.objects.assign((const int32_t*)(h + o_objects), (const int32_t*)(h + o_objects) + cap);
+	sel.people.assign((const int32_t*)(h + o_people), (const int32_t*)(h + o_people) + sel.n_people);
+	sel.groups.assign((const int32_t*)(h + o_groups), (const int32_t*)(h + o_groups) + sel.n_groups);
+	records.assign((const HmpObstacle*)(h + o_rec), (const HmpObstacle*)(h + o_rec) + cap * n_positions);
 	return HMP_OK;
 }
 
@@ -2143,25 +2169,27 @@ int hmp_build_environment(HmpContext* ctx, const HmpEnvParams* env, const double
 	EnvSelection sel;
 	int rc = env_select(ctx, *env, robot_pose, shapes, n_shapes, vertices_xy, n_vertices, people, n_people, groups, n_groups, 1, sel);
 	if (rc) return rc;
-	const int n_obj = (int)sel.objects.size();
+	// one launch over the capacity (the counts stay on the device), one synchronisation for selection + records
+	cudaStream_t st = ctx->stream;
+	std::vector<HmpObstacle> records;
+	CU(cudaMemcpyAsync(sel.d_positions, pose_ref, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+	if (sel.row_stride > 0) {
+		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, sel.d_counts, sel.row_stride, sel.d_positions, 1,
+		                              pose_ref[2], env, sel.d_out, st));
+		ctx->launches++;
+	}
+	if ((rc = env_read_back(ctx, sel, 1, records))) return rc;
+	const int n_obj = sel.counts[0] + sel.counts[1];
 	if (n_obj > *n_obstacles_out) {
 		set_err("environment model has %d objects, capacity %d", n_obj, *n_obstacles_out);
 		return HMP_E_CAPACITY;
 	}
-	cudaStream_t st = ctx->stream;
-	if (n_obj > 0) {
-		CU(cudaMemcpyAsync(sel.d_positions, pose_ref, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, n_obj, sel.d_positions, 1, pose_ref[2], env,
-		                              sel.d_out, st));
-		ctx->launches++;
-		CU(cudaMemcpyAsync(obstacles_out, sel.d_out, (size_t)n_obj * sizeof(HmpObstacle), cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-	}
+	std::copy(records.begin(), records.begin() + n_obj, obstacles_out);
 	*n_obstacles_out = n_obj;
-	std::copy(sel.people.begin(), sel.people.end(), people_selected);
-	*n_people_selected = (int)sel.people.size();
-	std::copy(sel.groups.begin(), sel.groups.end(), groups_selected);
-	*n_groups_selected = (int)sel.groups.size();
+	std::copy(sel.people.begin(), sel.people.begin() + sel.counts[1], people_selected);
+	*n_people_selected = sel.counts[1];
+	std::copy(sel.groups.begin(), sel.groups.begin() + sel.counts[2], groups_selected);
+	*n_groups_selected = sel.counts[2];
 	return HMP_OK;
 }
 
@@ -2182,17 +2210,17 @@ int hmp_compute_force_grid(HmpContext* ctx, const HmpEnvParams* env, const HmpWo
 	if ((rc = env_select(ctx, *env, robot_pose, shapes, n_shapes, vertices_xy, n_vertices, world->people, world->n_people, world->groups,
 	                     world->n_groups, n_positions, sel)))
 		return rc;
-	const int n_obj = (int)sel.objects.size();
 	cudaStream_t st = ctx->stream;
-	std::vector<HmpObstacle> records((size_t)n_obj * n_positions);
-	if (n_obj > 0) {
+	const int cap = sel.row_stride;
+	std::vector<HmpObstacle> records;
+	if (cap > 0) {
 		CU(cudaMemcpyAsync(sel.d_positions, positions_xy, (size_t)n_positions * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, n_obj, sel.d_positions, n_positions,
+		CU(hmp_dev_launch_env_closest(sel.d_shapes, sel.d_verts, sel.d_people, sel.d_objects, sel.d_counts, cap, sel.d_positions, n_positions,
 		                              world->robot_yaw, env, sel.d_out, st));
 		ctx->launches++;
-		CU(cudaMemcpyAsync(records.data(), sel.d_out, records.size() * sizeof(HmpObstacle), cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
 	}
+	if ((rc = env_read_back(ctx, sel, n_positions, records))) return rc;
+	const int n_obj = sel.counts[0] + sel.counts[1];
 	// one world per position: the robot there with the yaw of pose_, velocity vel_ rotated by pose_ (computeVelocityGlobal(vel_,
 	// pose_), humap_planner.cpp:654-656 -- the yaw is the same), goals unchanged; the motion model runs once with
 	// SampleAmplifierSet() and dt = sim_period (social_trajectory_generator.cpp:504-527)
@@ -2212,7 +2240,7 @@ int hmp_compute_force_grid(HmpContext* ctx, const HmpEnvParams* env, const HmpWo
 		HmpWorld& w = worlds[i];
 		w.robot_x = positions_xy[2 * i];
 		w.robot_y = positions_xy[2 * i + 1];
-		w.obstacles = n_obj > 0 ? records.data() + (size_t)i * n_obj : nullptr;
+		w.obstacles = n_obj > 0 ? records.data() + (size_t)i * cap : nullptr;
 		w.n_obstacles = n_obj;
 		w.people = nullptr;
 		w.n_people = 0;

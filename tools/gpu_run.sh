@@ -55,6 +55,6 @@ if [[ "$WHAT" == *" replay "* ]]; then
 fi
 if [[ "$WHAT" == *" prof1 "* ]]; then
   B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-cpu-baseline"
-  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:plan_kernel<0, double, 0" -s 2 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:plan_kernel<\(bool\)0, double, \(bool\)0' -s 2 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
   ls -la $OUT/${TAG}_full_mode1.ncu-rep
 fi
