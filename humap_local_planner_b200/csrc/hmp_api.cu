@@ -203,6 +203,7 @@ struct HmpContext {
 	HostBuf h_grid_stage[2];         // pinned staging of hmp_plan_batch's MapGrids (float), double-buffered
 	cudaEvent_t grid_stage_ev[2] = {nullptr, nullptr};
 	int sweep_layout = 0;            // FP32 sweep: 0 auto, 1 one warp per candidate, 2 one thread per candidate (hmp_set_sweep_layout)
+	int tpc_defer = 0;               // the last launch_main reserved shared memory for the deferred obstacle critic of the thread-per-candidate sweep
 	int last_sweep_mode = 0;         // launch mode of the last main sweep (0 warp per candidate, else threads per block of the thread-per-candidate kernel)
 
 	DevBuf d_seeds[HMP_NUM_MAPGRIDS];
@@ -213,7 +214,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec, d_posescr;
 	HostBuf h_stage, h_out;
 	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
@@ -660,11 +661,26 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		}
 	}
 	size_t smem_sweep = smem;
+	ctx->tpc_defer = 0;
 	if (tpc_threads) {
 		smem_sweep = smem + hmp_dev_tpc_extra_smem(pl.scene_stride);
 		if (smem_sweep > ctx->max_smem_optin) {
 			tpc_threads = 0;
 			smem_sweep = smem;
+		}
+	}
+	if (tpc_threads && ctx->prune_obstacle && D.scale[HMP_COST_OBSTACLE] != 0.0 && D.n_footprint > 0 && !D.occdist_sum &&
+	    !getenv("HMP_NO_DEFER")) {
+		// deferred obstacle critic: one byte per pose and thread behind the packed static objects; taken when it costs no
+		// resident block and the pose scratch (24 bytes per pose of one ticket per block) stays below 4 GiB
+		const size_t with = ((smem_sweep + 15) & ~(size_t)15) + (size_t)pl.T * tpc_threads;
+		int b0 = 0, b1 = 0;
+		const long long warps = (((long long)C + tpc_threads - 1) / tpc_threads) * pl.n_scenes * (tpc_threads / 32);
+		const int rich = (warps <= (long long)ctx->sm_count * 8 && !getenv("HMP_TPC_NO_RICH")) ? 1 : 0;
+		if (with <= ctx->max_smem_optin && hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, rich, &b0) == cudaSuccess &&
+		    hmp_dev_occupancy_tpc(with, tpc_threads, rich, &b1) == cudaSuccess && b1 >= b0 && b1 >= 1) {
+			smem_sweep = with;
+			ctx->tpc_defer = 1;
 		}
 	}
 	// few warps per SM sub-partition anyway (<= 2): the register-rich instance of the thread-per-candidate sweep
@@ -789,7 +805,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->wf_done[g]) cudaEventDestroy(ctx->wf_done[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask, &ctx->d_hvrec};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask, &ctx->d_hvrec, &ctx->d_posescr};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	for (int b = 0; b < 2; ++b) {
@@ -1236,7 +1252,15 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
 		A.best_init = E.best_out;
 	}
+	if (sweep_mode && ctx->tpc_defer && A.dilated) {
+		const size_t scr = (size_t)NS * blocks_x * (size_t)(sweep_mode & 1023) * T * 3 * sizeof(double);
+		if (scr <= ((size_t)4 << 30)) {
+			if ((rc = ctx->d_posescr.ensure(scr))) return rc;
+			A.pose_scratch = (double*)ctx->d_posescr.p;
+		}
+	}
 	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem_sweep, st));
+	A.pose_scratch = nullptr;   // the detail / refinement launches derived from A do not use it
 	ctx->launches++;
 	CU(cudaEventRecord(ctx->evm, st));
 	// snapshot the counters (n_generated, n_valid) before the detail pass reuses the work ticket

@@ -215,6 +215,10 @@ struct KernelArgs {
 	 * the largest valid cell value g looked up along the trajectory. Sweep launches only; null: not recorded. */
 	double* hv_pre;                  /* [n_scenes][n_candidates][4] */
 	float* hv_val;                   /* [n_scenes][n_candidates][4] */
+	/* Thread-per-candidate sweep, deferred obstacle critic: scratch for the poses (x, y, yaw as three planes of blockDim.x doubles per
+	 * step) of one ticket per block, [n_scenes][gridDim.x][T][3][blockDim.x]; null: the critic walks the footprint inside the rollout
+	 * loop. Needs `dilated`, the max aggregation and T * blockDim.x bytes of dynamic shared memory behind the packed static objects. */
+	double* pose_scratch;
 };
 
 #endif

@@ -346,6 +346,18 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 	const float obstacle_costs = (float)grid_cells;            // MapGrid::obstacleCosts()
 	const float unreachable_costs = (float)grid_cells + 1.0f;  // MapGrid::unreachableCellCosts()
 	const bool ob_on = P.scale[HMP_COST_OBSTACLE] != 0.0;
+	// Deferred obstacle critic (max aggregation with the dilated map): the rollout only records, per pose, the upper bound of
+	// its footprint cost (the dilated-map value) in shared memory and the pose itself in a global scratch; the footprints are
+	// walked after the horizon, poses in DESCENDING order of their bound, until the largest bound left cannot raise the maximum
+	// any more. The critic is a maximum over the poses (and "any pose negative" -> -6), so the order is free; walking the most
+	// expensive pose first prunes nearly all the others, where the in-loop test against the RUNNING maximum has to walk every
+	// pose of an approach to an obstacle (obstacle_separation_cost_function.cpp:85-114; bit-identical results).
+	const bool ob_defer = ob_on && A.pose_scratch != nullptr && dil != nullptr && !P.occdist_sum;
+	uint8_t* s_dmax = smem + ((L.total + 15u) & ~15u) + (HMP_TPC_PACKED ? ((A.scene_stride + 31u) & ~15u) : 0u);   // [T][blockDim.x]
+	double* pose_scr = ob_defer ? A.pose_scratch + ((size_t)scene * gridDim.x + blockIdx.x) * (size_t)P.T * 3 * blockDim.x : nullptr;
+	HMP_CHECK(!ob_defer || ((L.total + 15u) & ~15u) + (HMP_TPC_PACKED ? ((A.scene_stride + 31u) & ~15u) : 0u) + (uint32_t)P.T * blockDim.x <=
+	                           dynamic_smem_size(),
+	          "deferred obstacle critic: the per-pose bounds exceed the dynamic shared memory of the launch");
 
 	unsigned int* counters = A.counters + (size_t)scene * 4;
 	double tbest = -1.0;   // best of the candidates this thread has scored
@@ -410,6 +422,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 		float seed_x = 0.f, seed_w = 0.f;
 		bool ob_neg = false;
 		int ob_best = 0;
+		int ob_lb = 0;   // deferred critic: largest centre-cell cost so far, a lower bound of the final maximum
 		float ob_sum = 0.0f;
 		float mg_last[HMP_NUM_MAPGRIDS], mg_hv[HMP_NUM_MAPGRIDS];
 		int mg_codes = 0;   // 8 bits per grid: 0 ok, else -code
@@ -740,7 +753,27 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			// =============================== critics on pose i ==========================================
 			// ObstacleSeparationCostFunction (obstacle_separation_cost_function.cpp:85-114): the dilated-map test is per
 			// thread, the poses that must be rasterised are walked one after the other by the whole warp
-			{
+			if (ob_defer) {
+				if (alive) {
+					// bound of this pose's footprint cost; 255 (walk in any case) for a centre off the map. A pose whose bound
+					// does not exceed the centre-cell cost of an earlier pose (a lower bound of the final maximum) and holds
+					// nothing lethal / unknown can never matter: recorded as 0 = never walked.
+					int dm = 255, mx, my;
+					if (world_to_map(G, x, y, mx, my)) {
+						HMP_CHECK((size_t)(my * G.sx + mx) < grid_cells, "dilated-map look-up outside the map");
+						dm = (int)__ldg(&dil[my * G.sx + mx]);
+						if (dm <= ob_lb && dm < 254) dm = 0;
+						ob_lb = max(ob_lb, (int)cm[my * G.sx + mx]);
+					}
+					s_dmax[i * blockDim.x + tid] = (uint8_t)dm;
+					if (dm != 0) {
+						double* ps = pose_scr + (size_t)i * 3 * blockDim.x + tid;
+						ps[0] = x;
+						ps[blockDim.x] = y;
+						ps[2 * blockDim.x] = th;
+					}
+				}
+			} else {
 				bool need = alive && ob_on && !ob_neg;
 				if (need && dil != nullptr) {
 					int mx, my;
@@ -919,6 +952,53 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				ux = tgx_d;
 				uy = tgy_d;
 				uw = tw.w;
+			}
+		}
+
+		// ---- deferred obstacle critic: walk the recorded poses, largest bound first ----------------------
+		if (ob_defer) {
+			bool more = active && !rejected;   // a rejected sample is never scored; the others hold all T poses
+			for (;;) {
+				int sel = -1;
+				if (more) {
+					int selv = 0;
+					for (int i = 0; i < T; ++i) {
+						const int v = (int)s_dmax[i * blockDim.x + tid];
+						if (v > selv) {
+							selv = v;
+							sel = i;
+						}
+					}
+					// the same test as in the loop: nothing above the maximum so far and nothing lethal / unknown in reach
+					if (!(selv > ob_best || selv >= 254)) sel = -1;
+					if (sel < 0) more = false;
+				}
+				unsigned m = __ballot_sync(0xffffffffu, sel >= 0);
+				if (!m) break;
+				double px = 0.0, py = 0.0, pc = 1.0, ps = 0.0;
+				if (sel >= 0) {
+					const double* pp = pose_scr + (size_t)sel * 3 * blockDim.x + tid;
+					px = pp[0];
+					py = pp[blockDim.x];
+					sincos(pp[2 * blockDim.x], &ps, &pc);   // the rollout's own (cos, sin) of this yaw, bit for bit
+					s_dmax[sel * blockDim.x + tid] = 0;
+				}
+				while (m) {
+					const int src = __ffs(m) - 1;
+					m &= m - 1;
+					const double bx = __shfl_sync(0xffffffffu, px, src), by = __shfl_sync(0xffffffffu, py, src);
+					const double bc = __shfl_sync(0xffffffffu, pc, src), bs = __shfl_sync(0xffffffffu, ps, src);
+					bool neg = false;
+					int best = 0;
+					footprint_pose(P, G, cm, bx, by, bc, bs, lane, neg, best);
+					const bool any_neg = __any_sync(0xffffffffu, neg);
+					best = __reduce_max_sync(0xffffffffu, best);
+					if (lane == src) {
+						ob_neg = any_neg;
+						ob_best = max(ob_best, best);
+					}
+				}
+				if (ob_neg) more = false;   // -6 whatever the other poses hold
 			}
 		}
 
