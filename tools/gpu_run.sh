@@ -17,29 +17,29 @@ if [[ "$WHAT" == *" bench "* ]]; then
   tail -c 1500 $OUT/bench_$TAG.json; echo; tail -4 $OUT/bench_$TAG.err
 fi
 if [[ "$WHAT" == *" ab "* ]]; then
-  python bench.py --steps 10 --seeds 2 --no-config4 --no-cpu-baseline > $OUT/bench_ab_base_$TAG.json 2>> $OUT/ab_$TAG.err
+  python bench.py --steps 10 --seeds 2 --no-config4 --no-exact --no-cpu-baseline > $OUT/bench_ab_base_$TAG.json 2>> $OUT/ab_$TAG.err
   for d in tools/_ab/*/; do
     n=$(basename $d)
-    HMP_LIB=$d/libhmp_planner.so python bench.py --steps 10 --seeds 2 --no-config4 --no-cpu-baseline > $OUT/bench_ab_${n}_$TAG.json 2>> $OUT/ab_$TAG.err
+    HMP_LIB=$d/libhmp_planner.so python bench.py --steps 10 --seeds 2 --no-config4 --no-exact --no-cpu-baseline > $OUT/bench_ab_${n}_$TAG.json 2>> $OUT/ab_$TAG.err
   done
   for f in $OUT/bench_ab_*_$TAG.json; do echo "$f $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print('cycle', round(d['ms_per_step'],3), 'sweep', [round(r['sweep_ms'],3) for r in d['per_seed']], 'sel', d['selection_matches_reference'])" 2>&1 | tail -1)"; done
 fi
 if [[ "$WHAT" == *" ab1 "* ]]; then
-  B1="python bench.py --precise 1 --steps 6 --seeds 2 --no-config4 --no-cpu-baseline"
+  B1="python bench.py --precise 1 --steps 6 --seeds 2 --no-config4 --no-exact --no-cpu-baseline"
   $B1 > $OUT/bench_ab1_base_$TAG.json 2>> $OUT/ab1_$TAG.err
   for d in tools/_ab/*/; do
     n=$(basename $d)
     HMP_LIB=$d/libhmp_planner.so $B1 > $OUT/bench_ab1_${n}_$TAG.json 2>> $OUT/ab1_$TAG.err
-    HMP_LIB=$d/libhmp_planner.so python bench.py --steps 10 --seeds 2 --no-config4 --no-cpu-baseline > $OUT/bench_ab_${n}_$TAG.json 2>> $OUT/ab1_$TAG.err
+    HMP_LIB=$d/libhmp_planner.so python bench.py --steps 10 --seeds 2 --no-config4 --no-exact --no-cpu-baseline > $OUT/bench_ab_${n}_$TAG.json 2>> $OUT/ab1_$TAG.err
   done
   for f in $OUT/bench_ab1_*_$TAG.json $OUT/bench_ab_*_$TAG.json; do echo "$f $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print('cycle', round(d['ms_per_step'],3), 'sweep', [round(r['sweep_ms'],3) for r in d['per_seed']], 'sel', d['selection_matches_reference'])" 2>&1 | tail -1)"; done
 fi
 if [[ "$WHAT" == *" mode1 "* ]]; then
-  python bench.py --precise 1 --steps 6 --seeds 2 --no-config4 --no-cpu-baseline > $OUT/bench_mode1_$TAG.json 2> $OUT/bench_mode1_$TAG.err
+  python bench.py --precise 1 --steps 6 --seeds 2 --no-config4 --no-exact --no-cpu-baseline > $OUT/bench_mode1_$TAG.json 2> $OUT/bench_mode1_$TAG.err
   tail -c 700 $OUT/bench_mode1_$TAG.json; echo
 fi
 if [[ "$WHAT" == *" prof "* ]]; then
-  B="python bench.py --steps 2 --seeds 1 --warmup 3 --no-config4 --no-cpu-baseline"
+  B="python bench.py --steps 2 --seeds 1 --warmup 3 --no-config4 --no-exact --no-cpu-baseline"
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $B > $OUT/ncu_launches_$TAG.log 2>&1
   grep -c sweep_tpc $OUT/${TAG}_launches.csv
   ncu --set full --clock-control none --import-source on -k regex:sweep_tpc -s 4 -c 1 -f -o $OUT/${TAG}_full $B > $OUT/ncu_full_$TAG.log 2>&1
@@ -54,7 +54,7 @@ if [[ "$WHAT" == *" replay "* ]]; then
   tail -c 900 $OUT/bench_replay_$TAG.json; echo
 fi
 if [[ "$WHAT" == *" prof1 "* ]]; then
-  B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-cpu-baseline"
+  B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-exact --no-cpu-baseline"
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:plan_kernel<\(bool\)0, double, \(bool\)0' -s 2 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
   ls -la $OUT/${TAG}_full_mode1.ncu-rep
 fi
