@@ -623,7 +623,7 @@ def main():
         try:
             pl.set_precision(1)
             ex_rows, ex_ok = [], []
-            for seed in range(min(3, n_seeds)):
+            for seed in range(n_seeds):   # selection checked where a frozen reference winner exists (seeds 0..2)
                 sc = scenes.make_scene(cfg, seed=seed)
                 pl.set_costmap(sc.cells, sc.origin_x, sc.origin_y, sc.resolution)
                 for g in range(4):
@@ -634,7 +634,7 @@ def main():
                 if chk is not None:
                     ex_ok.append(bool(chk))
                 ms = []
-                for _ in range(3):
+                for _ in range(2):
                     flush.zero_()
                     torch.cuda.synchronize()
                     ms.append(pl.replan_resident()[0].gpu_ms)
@@ -642,10 +642,11 @@ def main():
                                 "best_total": float(r1.best_total)})
             ex_med = statistics.median([r["cycle_ms"] for r in ex_rows])
             line["exact_mode"] = {"dtype": "f64", "ms_per_step": ex_med, "value": C / (ex_med * 1e-3), "unit": UNIT,
-                                  "within_50ms_cycle": bool(max(r["cycle_ms"] for r in ex_rows) <= 50.0),
+                                  "max_cycle_ms": max(r["cycle_ms"] for r in ex_rows), "min_cycle_ms": min(r["cycle_ms"] for r in ex_rows),
+                                  "seeds_within_50ms": sum(1 for r in ex_rows if r["cycle_ms"] <= 50.0), "seeds": len(ex_rows),
                                   "selection_matches_reference": (all(ex_ok) if ex_ok else None), "per_seed": ex_rows,
                                   "what": "hmp_set_precision(1): FP64 object loops + FIS for every candidate (plan_kernel<false,double>), "
-                                          "one warp per candidate; resident inputs, CUDA events, median of 3 steps per seed, median over seeds"}
+                                          "one warp per candidate; resident inputs, CUDA events, median of 2 steps per seed, ms_per_step = median over the seeds"}
         except Exception as e:   # the headline line must not depend on it
             line["exact_mode"] = {"error": repr(e)}
     pl.close()

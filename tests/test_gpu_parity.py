@@ -876,6 +876,26 @@ def test_obstacle_pruning_is_exact(planner, name, seed, variant, layout):
     assert np.array_equal(np.array(a[3]), np.array(b[3]), equal_nan=True)
     assert np.array_equal(a[4], b[4])
     assert (a[4] >= 0).sum() > 0
+    if layout == 2:
+        # the thread-per-candidate sweep defers the critic behind the rollout (poses walked largest bound first); HMP_NO_DEFER=1
+        # (read at every plan) keeps the pruned walk inside the rollout loop: a third path to the same bits, incl. highest_valid_cost_
+        planner.set_precision(0)
+        planner.set_sweep_layout(layout)
+        planner.set_params(params)
+        planner.set_scene(sc)
+        if variant == "pentagon":
+            planner.set_footprint(_pentagon())
+        r0, _ = planner.plan(sc.world, smp)
+        t0 = planner.explored_totals(r0.n_candidates)
+        os.environ["HMP_NO_DEFER"] = "1"
+        try:
+            r1, _ = planner.plan(sc.world, smp)
+        finally:
+            os.environ.pop("HMP_NO_DEFER", None)
+        t1 = planner.explored_totals(r1.n_candidates)
+        assert r0.best_index == r1.best_index and r0.best_total == r1.best_total and r0.n_valid == r1.n_valid
+        assert list(r0.highest_valid_cost) == list(r1.highest_valid_cost)
+        assert np.array_equal(t0, t1) and np.array_equal(t0, a[4])
 
 
 # ---------------------------------------------------------------------------------------------------------------
