@@ -203,6 +203,7 @@ struct HmpContext {
 	HostBuf h_grid_stage[2];         // pinned staging of hmp_plan_batch's MapGrids (float), double-buffered
 	cudaEvent_t grid_stage_ev[2] = {nullptr, nullptr};
 	int sweep_layout = 0;            // FP32 sweep: 0 auto, 1 one warp per candidate, 2 one thread per candidate (hmp_set_sweep_layout)
+	int tpc_bps = 0;                 // resident blocks per SM of the last thread-per-candidate launch shape (launch_main)
 	int tpc_defer = 0;               // the last launch_main reserved shared memory for the deferred obstacle critic of the thread-per-candidate sweep
 	int last_sweep_mode = 0;         // launch mode of the last main sweep (0 warp per candidate, else threads per block of the thread-per-candidate kernel)
 
@@ -214,7 +215,7 @@ struct HmpContext {
 	bool seeds_event_valid[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	bool wavefront_pending[HMP_NUM_MAPGRIDS] = {false, false, false, false};
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
-	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec, d_posescr;
+	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec, d_posescr, d_poseslots;
 	HostBuf h_stage, h_out;
 	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
@@ -672,7 +673,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	if (tpc_threads && ctx->prune_obstacle && D.scale[HMP_COST_OBSTACLE] != 0.0 && D.n_footprint > 0 && !D.occdist_sum &&
 	    !getenv("HMP_NO_DEFER")) {
 		// deferred obstacle critic: one byte per pose and thread behind the packed static objects; taken when it costs no
-		// resident block and the pose scratch (24 bytes per pose of one ticket per block) stays below 4 GiB
+		// resident block (the pose scratch in global memory is one slot per resident block, run_cycle)
 		const size_t with = ((smem_sweep + 15) & ~(size_t)15) + (size_t)pl.T * tpc_threads;
 		int b0 = 0, b1 = 0;
 		const long long warps = (((long long)C + tpc_threads - 1) / tpc_threads) * pl.n_scenes * (tpc_threads / 32);
@@ -691,6 +692,7 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	}
 	int bps = 0;
 	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, tpc_rich, &bps));
+	if (tpc_threads) ctx->tpc_bps = bps;
 	else CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
 		set_err("kernel cannot be resident with %zu bytes of shared memory", smem);
@@ -805,7 +807,7 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->wf_done[g]) cudaEventDestroy(ctx->wf_done[g]);
 	}
 	DevBuf* bufs[] = {&ctx->d_params, &ctx->d_amp, &ctx->d_extra, &ctx->d_scenes, &ctx->d_costmaps, &ctx->d_mapgrids,
-	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask, &ctx->d_hvrec, &ctx->d_posescr};
+	                  &ctx->d_totals, &ctx->d_block_best, &ctx->d_ctrl, &ctx->d_detail, &ctx->d_dbg, &ctx->d_refine, &ctx->d_dilated, &ctx->d_equi, &ctx->d_env, &ctx->d_mask, &ctx->d_hvrec, &ctx->d_posescr, &ctx->d_poseslots};
 	for (DevBuf* b : bufs) b->release();
 	ctx->h_stage.release();
 	for (int b = 0; b < 2; ++b) {
@@ -1253,14 +1255,20 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		A.best_init = E.best_out;
 	}
 	if (sweep_mode && ctx->tpc_defer && A.dilated) {
-		const size_t scr = (size_t)NS * blocks_x * (size_t)(sweep_mode & 1023) * T * 3 * sizeof(double);
-		if (scr <= ((size_t)4 << 30)) {
-			if ((rc = ctx->d_posescr.ensure(scr))) return rc;
-			A.pose_scratch = (double*)ctx->d_posescr.p;
-		}
+		// deferred obstacle critic: one pose-scratch slot per block that can be resident at once (24 bytes per pose of one ticket)
+		const long long grid_blocks = (long long)NS * blocks_x;
+		const int n_slots = (int)std::min<long long>(grid_blocks, (long long)ctx->sm_count * std::max(1, ctx->tpc_bps));
+		const size_t scr = (size_t)n_slots * (size_t)(sweep_mode & 1023) * T * 3 * sizeof(double);
+		if ((rc = ctx->d_posescr.ensure(scr))) return rc;
+		if ((rc = ctx->d_poseslots.ensure((size_t)n_slots * sizeof(unsigned int)))) return rc;
+		CU(cudaMemsetAsync(ctx->d_poseslots.p, 0, (size_t)n_slots * sizeof(unsigned int), st));
+		A.pose_scratch = (double*)ctx->d_posescr.p;
+		A.pose_slots = (unsigned int*)ctx->d_poseslots.p;
+		A.pose_n_slots = n_slots;
 	}
 	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem_sweep, st));
 	A.pose_scratch = nullptr;   // the detail / refinement launches derived from A do not use it
+	A.pose_slots = nullptr;
 	ctx->launches++;
 	CU(cudaEventRecord(ctx->evm, st));
 	// snapshot the counters (n_generated, n_valid) before the detail pass reuses the work ticket

@@ -216,9 +216,15 @@ struct KernelArgs {
 	double* hv_pre;                  /* [n_scenes][n_candidates][4] */
 	float* hv_val;                   /* [n_scenes][n_candidates][4] */
 	/* Thread-per-candidate sweep, deferred obstacle critic: scratch for the poses (x, y, yaw as three planes of blockDim.x doubles per
-	 * step) of one ticket per block, [n_scenes][gridDim.x][T][3][blockDim.x]; null: the critic walks the footprint inside the rollout
+	 * step) of one ticket per block, [pose_n_slots][T][3][blockDim.x]; null: the critic walks the footprint inside the rollout
 	 * loop. Needs `dilated`, the max aggregation and T * blockDim.x bytes of dynamic shared memory behind the packed static objects. */
 	double* pose_scratch;
+	/* ... one scratch SLOT per resident block, not per block of the grid: a block takes a free slot when it starts (atomicCAS on
+	 * pose_slots, zeroed by the host before the launch; probing starts at its linear block index) and gives it back when it ends.
+	 * pose_n_slots >= blocks that can be resident at once, so a free slot always exists. */
+	unsigned int* pose_slots;
+	int32_t pose_n_slots;
+	int32_t _padp;
 };
 
 #endif

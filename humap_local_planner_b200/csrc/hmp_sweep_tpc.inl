@@ -193,11 +193,13 @@ __device__ __noinline__ StaticSum static_loop_packed(const float4* __restrict__ 
 // MINB = resident blocks per SM the registers are budgeted for: 2 (128 registers, 16 warps per SM) for launches that fill the
 // GPU, 1 (up to 255 registers: the kernel takes ~200 and loses its spills) for launches that leave at most two warps per SM
 // sub-partition anyway -- there a warp's speed is pure latency and the extra registers are free (cfg1: sweep 1.59 -> 1.52 ms).
+// DEFER: the instance with the deferred obstacle critic (launched when KernelArgs.pose_scratch is set); the other instance is
+// compiled without that code (its register pressure costs the few-object batched worlds of config 4 a quarter of their speed).
 #ifdef HMP_TPC_MAXNREG
-template <int MINB>
+template <int MINB, bool DEFER>
 __global__ void __maxnreg__(HMP_TPC_MAXNREG) sweep_tpc_kernel(const KernelArgs A) {
 #else
-template <int MINB>
+template <int MINB, bool DEFER>
 __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const KernelArgs A) {
 #endif
 	using R = float;
@@ -352,9 +354,19 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 	// any more. The critic is a maximum over the poses (and "any pose negative" -> -6), so the order is free; walking the most
 	// expensive pose first prunes nearly all the others, where the in-loop test against the RUNNING maximum has to walk every
 	// pose of an approach to an obstacle (obstacle_separation_cost_function.cpp:85-114; bit-identical results).
-	const bool ob_defer = ob_on && A.pose_scratch != nullptr && dil != nullptr && !P.occdist_sum;
+	const bool ob_defer = DEFER && ob_on && A.pose_scratch != nullptr && dil != nullptr && !P.occdist_sum;
 	uint8_t* s_dmax = smem + ((L.total + 15u) & ~15u) + (HMP_TPC_PACKED ? ((A.scene_stride + 31u) & ~15u) : 0u);   // [T][blockDim.x]
-	double* pose_scr = ob_defer ? A.pose_scratch + ((size_t)scene * gridDim.x + blockIdx.x) * (size_t)P.T * 3 * blockDim.x : nullptr;
+	// scratch slot of this block (one per RESIDENT block: the grid of a batch has thousands of blocks, a few hundred at a time)
+	__shared__ unsigned int s_slot;
+	if (ob_defer) {
+		if (tid == 0) {
+			unsigned int sl = (unsigned int)(((size_t)scene * gridDim.x + blockIdx.x) % (size_t)A.pose_n_slots);
+			while (atomicCAS(&A.pose_slots[sl], 0u, 1u) != 0u) sl = (sl + 1u == (unsigned int)A.pose_n_slots) ? 0u : sl + 1u;
+			s_slot = sl;
+		}
+		__syncthreads();
+	}
+	double* pose_scr = ob_defer ? A.pose_scratch + (size_t)s_slot * (size_t)P.T * 3 * blockDim.x : nullptr;
 	HMP_CHECK(!ob_defer || ((L.total + 15u) & ~15u) + (HMP_TPC_PACKED ? ((A.scene_stride + 31u) & ~15u) : 0u) + (uint32_t)P.T * blockDim.x <=
 	                           dynamic_smem_size(),
 	          "deferred obstacle critic: the per-pose bounds exceed the dynamic shared memory of the launch");
@@ -1134,6 +1146,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 		}
 	}
 	__syncthreads();
+	if (ob_defer && tid == 0) atomicExch(&A.pose_slots[s_slot], 0u);   // every thread of the block is past its last scratch access
 	if (tid == 0) {
 		double b = -1.0;
 		int bi = -1;

@@ -18,7 +18,7 @@ kern, name = [], None
 for ln in sass:
     if ln.startswith(".text."):
         name = ln
-    elif name and "sweep_tpc_kernelILi2E" in name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln) or (name and "sweep_tpc_kernelILi2E" in name and ln.startswith(".L_")):
+    elif name and "sweep_tpc_kernelILi2ELb1E" in name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln) or (name and "sweep_tpc_kernelILi2ELb1E" in name and ln.startswith(".L_")):
         kern.append(ln)
 ops = collections.Counter()
 for ln in kern:
