@@ -596,21 +596,32 @@ def main():
             "clocks": clocks,
             "selection_matches_reference": (all(selection.values()) if selection else None),
             "selection_checked_seeds": sorted(selection),
-            "roofline": {"bound": "fp32-cuda-core", "achieved": achieved, "peak": peak_fp32, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp32, "traffic": traffic,
-                         "algorithmic_frac": achieved / peak_fp32,
+            # frac = FP32 flop the kernel EXECUTED (ncu thread-level counts of the committed capture of this very kernel) over the
+            # live launch time, against the nominal CUDA-core peak. The algorithmic estimate of SURVEY 8d (what the reference's
+            # statements would cost) is reported beside it: the exact prunings (obstacle critic deferred and walked largest bound
+            # first, people-critic bounds) and the reformulations of DESIGN 3b skip most of it, so it can exceed the peak.
+            "roofline": {"bound": "fp32-cuda-core",
+                         "achieved": executed["tflops"] if executed else achieved,
+                         "peak": peak_fp32, "unit": "TFLOP/s",
+                         "frac": (executed["frac"] if executed else achieved / peak_fp32),
+                         "frac_is": "executed FP32 flop (ncu) / nominal peak" if executed else "algorithmic estimate / nominal peak",
+                         "traffic": traffic,
                          "executed_fp32_frac": executed["frac"] if executed else None,
                          "issue_active": executed["issue_active"] if executed else None,
                          "executed": executed,
-                         "peak_measured": peak_fp32_measured, "frac_of_measured": achieved / peak_fp32_measured,
+                         "algorithmic_frac": achieved / peak_fp32,
+                         "algorithmic": {"flop_per_candidate_step": W, "tflops": achieved, "over_nominal_peak": achieved / peak_fp32,
+                                         "over_measured_peak": achieved / peak_fp32_measured},
+                         "peak_measured": peak_fp32_measured,
+                         "frac_of_measured": (executed["tflops"] / peak_fp32_measured) if executed else achieved / peak_fp32_measured,
                          "hbm": {"achieved_gbs": (traffic / sel_s / 1e9) if traffic else None, "peak_gbs": hbm_peak},
-                         "note": f"algorithmic_frac (= frac): algorithmic flop per candidate-step W={W} (SURVEY.md 8d estimate of the "
-                                 f"reference's statements), per candidate T*W+60, over the live launch time of the dominant kernel {sweep_name} "
-                                 f"(median over seeds {1e3 * sel_s:.3f} ms); executed_fp32_frac: FP32 flop the kernel actually executed (ncu "
-                                 f"thread-level FFMA x2 + FMUL + FADD + MUFU of the committed capture) over the same time -- the prunings and "
-                                 f"reformulations of DESIGN 3b execute less than the estimate counts; issue_active: ncu smsp__issue_active. "
-                                 f"peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz; peak_measured = FFMA probe of this run "
-                                 "(MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is not HBM- or tensor-bound)"},
+                         "note": f"dominant kernel {sweep_name}, live launch time (median over seeds) {1e3 * sel_s:.3f} ms. executed: thread-level "
+                                 f"FFMA x2 + FMUL + FADD + MUFU of the committed ncu capture ({executed['source'] if executed else 'none'}); "
+                                 f"issue_active: ncu smsp__issue_active of that capture. algorithmic: W={W} flop per candidate-step (SURVEY.md 8d "
+                                 f"estimate of the reference's statements), per candidate T*W+60 -- a speed-up over the literal formulation at "
+                                 f"peak, not a utilisation. peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz; peak_measured = FFMA probe "
+                                 "of this run (MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is neither HBM- nor tensor-bound: "
+                                 "traffic is the DRAM bytes of the capture)"},
             "best_index": int(seed_rows[0]["best_index"]), "best_total": float(seed_rows[0]["best_total"]), "n_valid": int(seed_rows[0]["n_valid"]),
         }
         if not args.no_cpu_baseline:

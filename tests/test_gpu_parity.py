@@ -1242,10 +1242,9 @@ def test_refined_selection_equals_exact_mode_on_a_64k_replay(planner, lay):
 def test_refinement_with_a_bogus_fp32_best(planner):
     """64k candidates in the replay world, one warp per candidate: at plan 45 the FP32 best is a rollout whose FP32 total is
     5.9 % too LOW, so the 2 % window above it held nothing else and the refinement kept it (refined total 36.767) although
-    candidates just above the window beat it (36.421). The minimum leader count widens the first window and the second round
-    takes the window above the REFINED best; the winner of every plan is compared with the oracle's best among the 40 best
-    explored candidates. (A candidate whose own FP32 total is more than the window too HIGH and that ranks below the minimum
-    leader count stays out of reach: the documented limit of mode 2, allowed for on 2 of the 60 plans.)"""
+    candidates just above the window beat it (36.421). Since r02c the first round refines the K best-RANKED candidates (one wave
+    of FP64 rollouts, 1184 on a B200) and the second round the window above the REFINED best; the winner of every plan is
+    compared with the oracle's best among the 40 best explored candidates: no mismatch allowed."""
     from humap_local_planner_b200 import replay
     rows = []
 
@@ -1270,4 +1269,4 @@ def test_refinement_with_a_bogus_fp32_best(planner):
         planner.set_precision(False)
     assert log.parity_checked >= 50
     assert rows[45][1], rows[45]
-    assert log.parity_mismatch <= 2, [r for r in rows if not r[1]]
+    assert log.parity_mismatch == 0, [r for r in rows if not r[1]]

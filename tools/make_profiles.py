@@ -29,7 +29,7 @@ lib = os.path.join(ROOT, "humap_local_planner_b200", "lib", "libhmp_planner.so")
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = os.path.join(tmp, "hmp_kernels.sm_100a.cubin")
 with open(os.path.join(out, f"{tag}_ncu_by_line.txt"), "w") as f:
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), page, cubin, "sweep_tpc", "60", "0", "hmp_sweep_tpc.inl"],
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), page, cubin, "sweep_tpc_kernelILi2ELb1E", "60", "0", "hmp_sweep_tpc.inl"],
                    stdout=f, stderr=subprocess.STDOUT, cwd=ROOT)
 subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opcounts.py"), page, raw, os.path.join(out, f"{tag}_ncu_counts.json"),
                 f"ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 ({tag}), sweep_tpc_kernel"], check=True, stdout=subprocess.DEVNULL)
