@@ -402,7 +402,7 @@ size_t scene_blob_bytes(const HmpWorld& w) {
 }
 
 // Packs one World (+ people / groups) into `out` (scene_blob_bytes(w) bytes, zero-filled by the caller).
-void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev, double dt, unsigned char* out) {
+void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev, double dt, unsigned char* out, int n_equi = 0) {
 	const HmpParams& P = ctx->params;
 	DevScene H;
 	std::memset(&H, 0, sizeof(H));
@@ -429,6 +429,10 @@ void pack_scene(const HmpContext* ctx, const HmpWorld& w, const double* hv_prev,
 	H.gx = (float)(w.goal_x - w.robot_x);
 	H.gy = (float)(w.goal_y - w.robot_y);
 	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) H.hv_prev[g] = hv_prev ? hv_prev[g] : 0.0;
+	H.equi_px = (float)w.robot_x;   // Eigen::Vector3f pos_ of the equisampled generator (humap_planner.cpp:1317-1361)
+	H.equi_py = (float)w.robot_y;
+	H.equi_pth = (float)w.robot_yaw;
+	H.n_equi = n_equi;
 
 	std::vector<DevStatic> st_always, st_later;
 	std::vector<DevDynamic> dy_always, dy_first;
@@ -1251,7 +1255,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		E.block_best = A.block_best + (size_t)NS * blocks_x * 2;
 		CU(hmp_dev_launch_plan(&E, equi_blocks, 2, smem, st));
 		ctx->launches++;
-		CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, 2 * sizeof(unsigned int), st));   // work / done tickets; the counts accumulate
+		// work / done tickets of every scene back to zero; the counts (the other two words of a scene's four) accumulate
+		CU(cudaMemset2DAsync(ctrl + cl.off_counters, 4 * sizeof(unsigned int), 0, 2 * sizeof(unsigned int), (size_t)NS, st));
 		A.best_init = E.best_out;
 	}
 	if (sweep_mode && ctx->tpc_defer && A.dilated) {
@@ -1536,15 +1541,15 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 	if ((rc = ctx->h_stage.ensure(blob))) return rc;
 	CU(cudaStreamSynchronize(ctx->stream));
 	std::memset(ctx->h_stage.p, 0, blob);
-	pack_scene(ctx, *world, ctx->hv_prev, D.dt_d, (unsigned char*)ctx->h_stage.p);
-	uint32_t used = reinterpret_cast<DevScene*>(ctx->h_stage.p)->blob_bytes;
-	CU(cudaMemcpyAsync(ctx->d_scenes.p, ctx->h_stage.p, used, cudaMemcpyHostToDevice, ctx->stream));
 	std::vector<double> equi;
 	if (ctx->equi.enabled) {
 		equisampled_samples(ctx->params, *world, ctx->equi, D, equi);
 		D.n_equi = (int)(equi.size() / 3);
 		D.n_candidates = D.n_social + D.n_equi;
 	}
+	pack_scene(ctx, *world, ctx->hv_prev, D.dt_d, (unsigned char*)ctx->h_stage.p, D.n_equi);
+	uint32_t used = reinterpret_cast<DevScene*>(ctx->h_stage.p)->blob_bytes;
+	CU(cudaMemcpyAsync(ctx->d_scenes.p, ctx->h_stage.p, used, cudaMemcpyHostToDevice, ctx->stream));
 	PlanLaunch pl{1, used, n_extra, T};
 	return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
 }
@@ -1749,17 +1754,41 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 	CU(cudaStreamSynchronize(ctx->stream));
 	unsigned char* hs = (unsigned char*)ctx->h_stage.p;
 	std::memset(hs, 0, stride * n_scenes);
+	std::vector<std::vector<double>> equi_scene;
+	std::vector<double> equi_all;
 	{
 		// scene blobs packed by the host threads (a 4096-world batch is ~12 MB of records)
 		const unsigned nt = (unsigned)std::max(1, std::min<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), n_scenes / 64 + 1));
+		// second generator of the pool (hmp_set_equisampled): every world has its own velocity window, hence its own samples and,
+		// where the window spans zero, its own sample count; the batch takes the largest count and pads (DevScene.n_equi)
+		const bool with_equi = ctx->equi.enabled != 0;
+		if (with_equi) equi_scene.resize((size_t)n_scenes);
 		auto work = [&](unsigned t) {
-			for (int s = (int)t; s < n_scenes; s += (int)nt)
-				pack_scene(ctx, worlds[s], highest_valid_cost_prev ? highest_valid_cost_prev + 4 * (size_t)s : nullptr, D.dt_d, hs + stride * s);
+			DevParams Dt = D;   // equisampled_samples also fills the (shared) acceleration limits; the per-thread copy is discarded
+			for (int s = (int)t; s < n_scenes; s += (int)nt) {
+				int ne = 0;
+				if (with_equi) {
+					equisampled_samples(ctx->params, worlds[s], ctx->equi, Dt, equi_scene[(size_t)s]);
+					ne = (int)(equi_scene[(size_t)s].size() / 3);
+				}
+				pack_scene(ctx, worlds[s], highest_valid_cost_prev ? highest_valid_cost_prev + 4 * (size_t)s : nullptr, D.dt_d, hs + stride * s, ne);
+			}
 		};
 		std::vector<std::thread> pool;
 		for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
 		work(0);
 		for (auto& th : pool) th.join();
+		if (with_equi) {
+			std::vector<double> dummy;
+			equisampled_samples(ctx->params, worlds[0], ctx->equi, D, dummy);   // acceleration limits / continued flag into D
+			size_t ne_max = 0;
+			for (const auto& v : equi_scene) ne_max = std::max(ne_max, v.size() / 3);
+			equi_all.assign((size_t)n_scenes * ne_max * 3, 0.0);
+			for (int s = 0; s < n_scenes; ++s)
+				std::copy(equi_scene[(size_t)s].begin(), equi_scene[(size_t)s].end(), equi_all.begin() + (size_t)s * ne_max * 3);
+			D.n_equi = (int)ne_max;
+			D.n_candidates = D.n_social + D.n_equi;
+		}
 	}
 	CU(cudaMemcpyAsync(ctx->d_scenes.p, hs, stride * n_scenes, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
@@ -1825,7 +1854,7 @@ int hmp_plan_batch(HmpContext* ctx, const HmpWorld* worlds, int32_t n_scenes, co
 		ctx->batch_grid_scenes = n_scenes;
 	}
 	PlanLaunch pl{n_scenes, (uint32_t)stride, 0, T};
-	return run_cycle(ctx, D, amp_table, nullptr, 0, std::vector<double>(), pl, results, nullptr, 0);
+	return run_cycle(ctx, D, amp_table, nullptr, 0, equi_all, pl, results, nullptr, 0);
 }
 
 // Re-runs the selection of the last plan on the data still resident on the device (no host<->device

@@ -98,6 +98,11 @@ struct alignas(16) DevScene {
 	uint32_t blob_bytes;          /* header + arrays, multiple of 16                                   */
 	int32_t _pad;
 	double hv_prev[HMP_NUM_MAPGRIDS];   /* highest_valid_cost_prev_ per MapGrid critic                    */
+	/* equisampled generator (SimpleTrajectoryGenerator): Eigen::Vector3f pos_ of this scene (float stores of the UNWRAPPED pose;
+	 * vel_ is vlx / vly / vlw above) and the number of its velocity samples -- the scenes of a batch share n_equi of DevParams
+	 * (the largest count); candidates beyond a scene's own count are padding and count as rejected by the generator */
+	float equi_px, equi_py, equi_pth;
+	int32_t n_equi;
 };
 
 /* Flattened HumapConfig for the device: FP32 where the arithmetic is FP32, FP64 where the reference's
@@ -171,7 +176,7 @@ struct KernelArgs {
 	const DevParams* params;         /* device */
 	const double* amp_values;        /* [10][HMP_MAX_AMP_VALUES] device                           */
 	const double* extra_samples;     /* [n_extra][10] device, or null                             */
-	const double* equi_samples;      /* [n_equi][3] target velocities (float values), or null      */
+	const double* equi_samples;      /* [n_scenes][n_equi][3] target velocities (float values), or null */
 	const uint8_t* scenes;           /* n_scenes blobs, stride scene_stride bytes                  */
 	uint32_t scene_stride;
 	int32_t n_scenes;

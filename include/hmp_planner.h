@@ -380,8 +380,8 @@ int hmp_compute_mapgrid(HmpContext* ctx, int32_t grid, const double* plan_xy, in
 int hmp_get_mapgrid(HmpContext* ctx, int32_t grid, double* target_dist_out);
 
 /* Replaces generator_vel_space_.setParameters (humap_planner.cpp:196-203) + the per-cycle initialise (:1317-1361) of the
- * equisampled generator for the following hmp_plan calls (single-scene plans; NULL or enabled = 0 turns it off, which
- * is the state after hmp_create). The velocity window is derived per cycle from HmpLimits, HmpGeneral (sim_time,
+ * equisampled generator for the following hmp_plan / hmp_plan_batch calls (NULL or enabled = 0 turns it off, which
+ * is the state after hmp_create; in a batch every world gets its own velocity window and samples). The velocity window is derived per cycle from HmpLimits, HmpGeneral (sim_time,
  * sim_period), the robot velocity and the goal of the HmpWorld, as the reference does. */
 int hmp_set_equisampled(HmpContext* ctx, const HmpEquisampled* eq);
 /* Replaces ObstacleSeparationCostFunction::setFootprint (humap_planner.cpp:1059); xy interleaved. */

@@ -828,6 +828,47 @@ def test_refined_batch_equals_single_cycles(planner, layout):
         assert abs(r.best_total - bt) <= 1e-12 * max(1.0, abs(bt))
 
 
+@pytest.mark.parametrize("precise", [1, 2], ids=["fp64", "refine"])
+def test_batch_with_equisampled_pool_equals_single_plans(planner, precise, layout):
+    """hmp_plan_batch with the second generator of the pool (SimpleTrajectoryGenerator, humap_planner.cpp:85-95, :1317-1361):
+    every world of the batch has its own velocity window -- and, where the window spans zero, its own sample count (the
+    batch pads to the largest) -- and must select what a single-scene plan of that world selects."""
+    if precise == 1 and layout == 2:
+        pytest.skip("the FP64 sweep has one layout")
+    cfg = scenes.CONFIGS["cfg0"]
+    params = scenes.make_params(cfg)
+    smp = scenes.make_sampling(cfg)
+    vels = [(0.3, 0.0, 0.0), (0.9, 0.0, -0.4), (0.0, 0.0, 0.0), (0.05, 0.0, 0.1), (1.2, 0.0, 0.2)]
+    scs = [scenes.make_scene(cfg, 10 + k, base_vel=v) for k, v in enumerate(vels)]
+    eq = _equi(continued=0)   # DWA window (sim_period): spans zero yaw rate for some of the worlds only -> 10 or 11 yaw-rate samples
+    planner.set_precision(precise)
+    planner.set_sweep_layout(layout)
+    try:
+        planner.set_params(params)
+        planner.set_equisampled(eq)
+        singles = []
+        for sc in scs:
+            planner.set_scene(sc)
+            r, _ = planner.plan(sc.world, smp)
+            singles.append((r.best_index, r.best_total, r.n_candidates, r.n_generated, r.n_valid))
+        planner.set_scene(scs[0])
+        cells = np.stack([sc.cells for sc in scs])
+        grids = [np.stack([sc.grids[g] for sc in scs]) for g in range(4)]
+        hv = np.array([sc.hv_prev for sc in scs])
+        res = planner.plan_batch([sc.world for sc in scs], cells, grids, smp, hv_prev=hv)
+    finally:
+        planner.set_equisampled(None)
+        planner.set_sweep_layout(0)
+        planner.set_precision(False)
+    n_max = max(s[2] for s in singles)
+    assert len({s[2] for s in singles}) > 1, "the worlds were meant to differ in their sample counts"
+    for k, ((bi, bt, nc, ng, nv), r) in enumerate(zip(singles, res)):
+        assert r.n_candidates == n_max
+        assert (r.best_index, r.n_generated, r.n_valid) == (bi, ng, nv), (k, r.best_index, bi, r.n_generated, ng, r.n_valid, nv)
+        assert abs(r.best_total - bt) <= 1e-12 * max(1.0, abs(bt))
+    print("winners", [s[0] for s in singles], "pool sizes", [s[2] for s in singles])
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # exact pruning of the obstacle critic (dilated max-cost map): results must be bit-identical with and without it
 # ---------------------------------------------------------------------------------------------------------------
