@@ -23,6 +23,9 @@
 #define HMP_TPC_UNROLL 2
 #endif
 
+#ifndef HMP_TPC_ESTRIN
+#define HMP_TPC_ESTRIN 0   /* 1: the asin polynomial of the packed loops by Estrin's scheme (A/B) */
+#endif
 #ifndef HMP_TPC_PACKED
 #define HMP_TPC_PACKED 1   /* static-object loop in packed FP32x2 arithmetic (FFMA2 / FADD2 / FMUL2 of sm_100), two objects per iteration */
 #endif
@@ -35,6 +38,19 @@ __device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
 	const bool lo_x = s.x <= fabsf(c.x), lo_y = s.y <= fabsf(c.y);
 	const float2 z = make_float2(lo_x ? s.x : c.x, lo_y ? s.y : c.y);
 	const float2 q = __fmul2_rn(z, z);
+#if HMP_TPC_ESTRIN
+	// Estrin's scheme: the same degree-8 polynomial with a dependency depth of 4 instead of 9 (two more multiplications)
+	const float2 q2 = __fmul2_rn(q, q);
+	const float2 q4 = __fmul2_rn(q2, q2);
+	const float2 e01 = __ffma2_rn(bc2(1.666642890e-01f), q, bc2(1.000000020e+00f));
+	const float2 e23 = __ffma2_rn(bc2(4.341339492e-02f), q, bc2(7.508057529e-02f));
+	const float2 e45 = __ffma2_rn(bc2(-2.460549290e-02f), q, bc2(4.040429929e-02f));
+	const float2 e67 = __ffma2_rn(bc2(-1.801251085e-01f), q, bc2(1.457034517e-01f));
+	const float2 e03 = __ffma2_rn(e23, q2, e01);
+	const float2 e47 = __ffma2_rn(e67, q2, e45);
+	const float2 e8 = __fmul2_rn(bc2(1.448995462e-01f), q4);
+	float2 p = __ffma2_rn(__ffma2_rn(e8, q4, e47), q4, e03);   // (c8 q^4 * q^4 + e47) q^4 + e03
+#else
 	float2 p = bc2(1.448995462e-01f);
 	p = __ffma2_rn(p, q, bc2(-1.801251085e-01f));
 	p = __ffma2_rn(p, q, bc2(1.457034517e-01f));
@@ -44,6 +60,7 @@ __device__ __forceinline__ float2 angle_from_cos_sin2(float2 c, float2 s) {
 	p = __ffma2_rn(p, q, bc2(7.508057529e-02f));
 	p = __ffma2_rn(p, q, bc2(1.666642890e-01f));
 	p = __ffma2_rn(p, q, bc2(1.000000020e+00f));
+#endif
 	float2 r = __fmul2_rn(z, p);   // asin(z), signed
 	// s <= |c|: the angle is asin(s) in front (c >= 0) and pi - asin(s) behind; otherwise acos(c) = pi/2 - asin(c)
 	r.x = lo_x ? ((c.x < 0.0f) ? PI_F - r.x : r.x) : 1.57079632679489662f - r.x;
