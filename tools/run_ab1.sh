@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out; TAG=$1
 mkdir -p $OUT
-B1="python bench.py --precise 1 --steps 6 --seeds 2 --no-config4 --no-cpu-baseline"
+B1="python bench.py --precise 1 --steps 6 --seeds 3 --no-config4 --no-cpu-baseline"
 $B1 > $OUT/bench_ab1_base_$TAG.json 2>> $OUT/ab1_$TAG.err
 for d in tools/_ab/*/; do
   n=$(basename $d)
