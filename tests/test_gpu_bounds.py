@@ -49,6 +49,12 @@ pl.set_params(scenes.make_params(cfg3)); pl.set_scene(scs[0])
 rb = pl.plan_batch([s.world for s in scs], np.stack([s.cells for s in scs]), [np.stack([s.grids[q] for s in scs]) for q in range(4)],
                    scenes.make_sampling(cfg3), hv_prev=np.array([s.hv_prev for s in scs]))
 out["batch"] = [[r.best_index, r.best_total] for r in rb]
+# the same batch with the second generator of the pool (per-world velocity windows, padded sample lists)
+eq.vth_samples, eq.continued_acceleration = 10, 0
+pl.set_equisampled(eq)
+rb = pl.plan_batch([s.world for s in scs], None, None, scenes.make_sampling(cfg3), hv_prev=np.array([s.hv_prev for s in scs]))
+out["batch-equi"] = [[r.best_index, r.best_total, r.n_candidates] for r in rb]
+pl.set_equisampled(None)
 pl.close()
 print("RESULT " + json.dumps(out))
 '''
