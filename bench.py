@@ -542,6 +542,23 @@ def main():
         flops_cand, W = algorithmic_flops_per_candidate(cfg, params, ns, nd, bool(args.fis), T)
         sel_s = med_sweep * 1e-3
         achieved = C * flops_cand / sel_s / 1e12
+        # INSTRUMENTED operation count of the reference formulation (tools/count_flops.py: the oracle over a counting scalar, a
+        # 512-candidate sample per seed, committed as profiles/r02_flop_count.json -- only the JSON is read here): flop one cycle
+        # of the CPU path executes for this world, rejections included, over this run's sweep time of the same seed
+        instrumented = None
+        try:
+            fc = json.load(open(os.path.join(ROOT, "profiles", "r02_flop_count.json")))
+            per_seed_flop = {r["seed"]: r for r in fc["rows"] if r["config"] == args.cfg}
+            tf_rows = [per_seed_flop[row["seed"]]["flop_per_cycle"] / (row["sweep_ms"] * 1e-3) / 1e12
+                       for row in seed_rows if row["seed"] in per_seed_flop]
+            if tf_rows and bool(args.fis):
+                med = fc["median_over_seeds"][args.cfg]
+                instrumented = {"flop_per_candidate_step": med["flop_per_candidate_step"], "flop_per_cycle": med["flop_per_cycle"],
+                                "tflops": statistics.median(tf_rows), "seeds": len(tf_rows),
+                                "survey_estimate_over_instrumented": W / med["flop_per_candidate_step"],
+                                "source": "profiles/r02_flop_count.json (tools/count_flops.py)"}
+        except Exception:
+            instrumented = None
         mode = pl.last_sweep_mode()
         sweep_name = (f"sweep_tpc_kernel (one thread per candidate, {mode} threads per block)" if mode
                       else ("plan_kernel<false,double> (one warp per candidate, FP64)" if int(args.precise) == 1
@@ -609,17 +626,23 @@ def main():
                          "executed_fp32_frac": executed["frac"] if executed else None,
                          "issue_active": executed["issue_active"] if executed else None,
                          "executed": executed,
-                         "algorithmic_frac": achieved / peak_fp32,
-                         "algorithmic": {"flop_per_candidate_step": W, "tflops": achieved, "over_nominal_peak": achieved / peak_fp32,
-                                         "over_measured_peak": achieved / peak_fp32_measured},
+                         "algorithmic_frac": (instrumented["tflops"] if instrumented else achieved) / peak_fp32,
+                         "algorithmic_frac_is": ("instrumented flop count of the reference formulation / sweep time / nominal peak"
+                                                 if instrumented else "SURVEY 8d estimate / sweep time / nominal peak"),
+                         "algorithmic": {"instrumented": instrumented,
+                                         "survey_estimate": {"flop_per_candidate_step": W, "tflops": achieved,
+                                                             "over_nominal_peak": achieved / peak_fp32,
+                                                             "over_measured_peak": achieved / peak_fp32_measured}},
                          "peak_measured": peak_fp32_measured,
                          "frac_of_measured": (executed["tflops"] / peak_fp32_measured) if executed else achieved / peak_fp32_measured,
                          "hbm": {"achieved_gbs": (traffic / sel_s / 1e9) if traffic else None, "peak_gbs": hbm_peak},
                          "note": f"dominant kernel {sweep_name}, live launch time (median over seeds) {1e3 * sel_s:.3f} ms. executed: thread-level "
                                  f"FFMA x2 + FMUL + FADD + MUFU of the committed ncu capture ({executed['source'] if executed else 'none'}); "
-                                 f"issue_active: ncu smsp__issue_active of that capture. algorithmic: W={W} flop per candidate-step (SURVEY.md 8d "
-                                 f"estimate of the reference's statements), per candidate T*W+60 -- a speed-up over the literal formulation at "
-                                 f"peak, not a utilisation. peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz; peak_measured = FFMA probe "
+                                 f"issue_active: ncu smsp__issue_active of that capture. algorithmic.instrumented: flop the CPU formulation executes "
+                                 f"per cycle, counted by running the oracle over a counting scalar (add, mul, div, sqrt, exp, trig, atan2 one "
+                                 f"each), over the sweep time -- how much of the literal formulation's work per second the kernel delivers, not a "
+                                 f"utilisation (prunings and reformulations skip part of it); survey_estimate: W={W} flop per candidate-step "
+                                 f"(SURVEY.md 8d, read off the reference's statements; 1.4-1.9x the instrumented count). peak = nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz; peak_measured = FFMA probe "
                                  "of this run (MEASURED_PEAKS.json has no FP32 CUDA-core entry; the path is neither HBM- nor tensor-bound: "
                                  "traffic is the DRAM bytes of the capture)"},
             "best_index": int(seed_rows[0]["best_index"]), "best_total": float(seed_rows[0]["best_total"]), "n_valid": int(seed_rows[0]["n_valid"]),

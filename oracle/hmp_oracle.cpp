@@ -32,6 +32,10 @@
 #include <array>
 #include <vector>
 
+#ifndef HMP_ORACLE_COUNT
+typedef double orc_f64;   // the plain IEEE double, also in the counting build (hmp_oracle_count.cpp), where `double` is a macro
+#endif
+
 namespace {
 
 constexpr double PI = 3.14159265358979323846;  // IGN_PI
@@ -311,7 +315,7 @@ struct Robot {
 	double heading_dir = 0;
 };
 
-constexpr double RELATIVE_LOCATION_FRONT_THRESHOLD = 9.0 * PI / 180.0;  // world.h:97
+const double RELATIVE_LOCATION_FRONT_THRESHOLD = 9.0 * PI / 180.0;  // world.h:97
 constexpr double SPEED_THRESHOLD_STATIONARY_ROBOT = 0.01;               // world.h:104
 constexpr double SPEED_THRESHOLD_STATIONARY_OBJECT = 0.035;             // world.h:110
 
@@ -622,7 +626,7 @@ inline FlTerm triangle_deg(double a, double b, double c) { return {dtor(a), dtor
 inline double quantize6(double v) {
 	if (std::isnan(v)) return v;
 	char buf[64];
-	std::snprintf(buf, sizeof(buf), "%f", v);
+	std::snprintf(buf, sizeof(buf), "%f", (orc_f64)v);
 	return std::strtod(buf, nullptr);
 }
 
@@ -1108,7 +1112,7 @@ void mapgridCompute(const Costmap& cm, const double* plan_xy, int n_plan, bool l
 		double loop_x = plan_xy[2 * i], loop_y = plan_xy[2 * i + 1];
 		double sqdist = (loop_x - last_x) * (loop_x - last_x) + (loop_y - last_y) * (loop_y - last_y);
 		if (sqdist > min_sq_resolution) {
-			int steps = std::ceil((std::sqrt(sqdist)) / cm.resolution);
+			int steps = (int)std::ceil((std::sqrt(sqdist)) / cm.resolution);
 			double deltax = (loop_x - last_x) / steps;
 			double deltay = (loop_y - last_y) / steps;
 			for (int j = 1; j < steps; ++j) {
@@ -1616,7 +1620,7 @@ double scoreTrajectoryAll(PlanState& st, const BlpTrajectory& traj, double best_
 // :465-498
 std::vector<double> computeAmplifierSamples(double amp_min, double amp_max, double granularity) {
 	std::vector<double> samples;
-	int num_amps = std::ceil((amp_max - amp_min) / granularity);
+	int num_amps = (int)std::ceil((amp_max - amp_min) / granularity);
 	for (int i = 0; i <= num_amps; i++) {
 		double v = amp_min + granularity * i;
 		if (v > amp_max) {
@@ -1644,7 +1648,7 @@ std::vector<HmpSample> buildSamples(const HmpSampling& s, const HmpSample* extra
 		size_t rem = idx;
 		for (int a = HMP_NUM_AMPLIFIERS - 1; a >= 0; --a) {
 			size_t n = lists[a].size();
-			smp.amp[a] = lists[a][rem % n];
+			smp.amp[a] = (orc_f64)lists[a][rem % n];
 			rem /= n;
 		}
 		out.push_back(smp);
@@ -1660,7 +1664,7 @@ int computeStepsNumber(const HmpGeneral& g, double speed_linear, double speed_an
 	}
 	double sim_time_distance = speed_linear * g.sim_time;
 	double sim_time_angle = std::fabs(speed_angular) * g.sim_time;
-	return std::ceil(std::max(sim_time_distance / g.sim_granularity, sim_time_angle / g.angular_sim_granularity));
+	return (int)std::ceil(std::max(sim_time_distance / g.sim_granularity, sim_time_angle / g.angular_sim_granularity));
 }
 
 // :556-582
@@ -2003,9 +2007,9 @@ EnvModel createEnvironmentModel(const HmpEnvParams& env, const double robot_pose
 	auto emit = [&](const Pose& r, const Pose& o, double vx, double vy, double vth, bool force_dynamic) {
 		HmpObstacle ob;
 		std::memset(&ob, 0, sizeof(ob));
-		ob.robot_x = r.x; ob.robot_y = r.y; ob.robot_yaw = r.yaw;
-		ob.obj_x = o.x; ob.obj_y = o.y; ob.obj_yaw = o.yaw;
-		ob.vx = vx; ob.vy = vy; ob.vth = vth;
+		ob.robot_x = (orc_f64)r.x; ob.robot_y = (orc_f64)r.y; ob.robot_yaw = (orc_f64)r.yaw;
+		ob.obj_x = (orc_f64)o.x; ob.obj_y = (orc_f64)o.y; ob.obj_yaw = (orc_f64)o.yaw;
+		ob.vx = (orc_f64)vx; ob.vy = (orc_f64)vy; ob.vth = (orc_f64)vth;
 		ob.force_dynamic = force_dynamic ? 1 : 0;
 		m.obstacles.push_back(ob);
 	};
@@ -2142,11 +2146,11 @@ struct EquiGenerator {
 		if (max_vel_trans >= 0 && vmag - eps > max_vel_trans) return false;
 		int num_steps;
 		if (discretize_by_time) {
-			num_steps = std::ceil(sim_time / sim_granularity);
+			num_steps = (int)std::ceil(sim_time / sim_granularity);
 		} else {
 			double sim_time_distance = vmag * sim_time;
 			double sim_time_angle = std::fabs(target[2]) * sim_time;
-			num_steps = std::ceil(std::max(sim_time_distance / sim_granularity, sim_time_angle / angular_sim_granularity));
+			num_steps = (int)std::ceil(std::max(sim_time_distance / sim_granularity, sim_time_angle / angular_sim_granularity));
 		}
 		if (num_steps == 0) return false;
 		double dt = sim_time / num_steps;
@@ -2303,6 +2307,7 @@ void buildScene(PlanState& st, const HmpParams& P, const HmpWorld& hw) {
 // ================================================================================================
 // C API
 // ================================================================================================
+#ifndef HMP_ORACLE_COUNT   /* hmp_oracle_count.cpp compiles everything above with a counting scalar and brings its own entry point */
 extern "C" {
 
 int orc_num_candidates(const HmpSampling* sampling, int n_extra) {
@@ -2834,3 +2839,4 @@ double orc_tp_footprint_cost(const uint8_t* cells, int size_x, int size_y, doubl
 }
 
 }  // extern "C"
+#endif  // HMP_ORACLE_COUNT

@@ -273,3 +273,34 @@ def plan_all_threaded(params, scene, sampling, n_threads=None, want=("totals",))
     with cf.ThreadPoolExecutor(n_threads) as ex_:
         list(ex_.map(work, range(len(bounds) - 1)))
     return totals
+
+
+OP_NAMES = ("add", "mul", "div", "sqrt", "exp", "trig", "atan2", "cmp", "rnd")
+_count_lib = None
+
+
+def count_ops(params, scene, sampling, indices):
+    """Instrumented floating-point operation count of the oracle (oracle/hmp_oracle_count.cpp: the oracle's source text over a
+    counting scalar) for the listed social candidates. Returns a dict: ops_rollout / ops_scoring (name -> count, summed over
+    the candidates), steps_rolled, n_generated, totals (bit-identical to orc_plan's)."""
+    global _count_lib
+    if _count_lib is None:
+        path = os.path.join(ROOT, "oracle", "_build", "libhmp_oracle_count.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        _count_lib = C.CDLL(path)
+        _count_lib.orc_count_plan.restype = C.c_int
+        _count_lib.orc_count_plan.argtypes = [C.POINTER(OrcPlanInput), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        assert _count_lib.orc_count_num_ops() == len(OP_NAMES)
+    idx = np.ascontiguousarray(indices, dtype=np.int32)
+    inp = _make_input(params, scene, sampling, None, 0, False, (0, 0), None)
+    ro = np.zeros(len(OP_NAMES), dtype=np.uint64)
+    sc = np.zeros(len(OP_NAMES), dtype=np.uint64)
+    steps = np.zeros(1, dtype=np.uint64)
+    ngen = np.zeros(1, dtype=np.int32)
+    totals = np.full(len(idx), np.nan)
+    rc = _count_lib.orc_count_plan(C.byref(inp), _p(idx), len(idx), _p(ro), _p(sc), _p(steps), _p(ngen), _p(totals))
+    assert rc == 0
+    return {"ops_rollout": {n: int(v) for n, v in zip(OP_NAMES, ro)}, "ops_scoring": {n: int(v) for n, v in zip(OP_NAMES, sc)},
+            "steps_rolled": int(steps[0]), "n_generated": int(ngen[0]), "totals": totals}
