@@ -55,6 +55,7 @@ extern "C" cudaError_t hmp_dev_launch_hv_early_exit(const double* totals, const 
 extern "C" cudaError_t hmp_dev_launch_collect_topk(const double* totals, int C, const double* best_out, int K, double round2_window,
                                                    int32_t* leaders, int32_t* count, double* thr_out, int n_scenes, const int32_t* active,
                                                    cudaStream_t stream);
+extern "C" cudaError_t hmp_dev_launch_fill_leaders(int32_t* leaders, int K, int C, int32_t* count, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_reselect(const double* totals, int C, double* best_out, const int32_t* active, int n_scenes,
                                                cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int K, int C, int T, const double* r_totals,
@@ -167,6 +168,9 @@ struct HmpContext {
 	int sm_count = 0;
 	size_t max_smem_optin = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t stream2 = nullptr;   // FP64 rollouts of a small pool, beside the FP32 sweep (run_cycle)
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	int overlap_refine = 1;           // HMP_NO_OVERLAP=1 in the environment: the refinement follows the sweep (A/B)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
 	int64_t launches = 0;
 
@@ -217,6 +221,7 @@ struct HmpContext {
 	int n_seeds[HMP_NUM_MAPGRIDS] = {0, 0, 0, 0};
 	DevBuf d_params, d_amp, d_extra, d_scenes, d_costmaps, d_mapgrids, d_totals, d_block_best, d_ctrl, d_detail, d_dbg, d_refine, d_dilated, d_equi, d_env, d_mask, d_hvrec, d_posescr, d_poseslots;
 	HostBuf h_stage, h_out;
+	HostBuf h_small;   // pinned words read back inside a cycle: [0..3] overflow status of the four wave fronts, [4..5] leader counts
 	HostBuf h_grid[HMP_NUM_MAPGRIDS];   // pinned staging of hmp_set_mapgrid, one per slot
 	uint32_t costmap_stride = 0;
 
@@ -600,7 +605,8 @@ void equisampled_samples(const HmpParams& P, const HmpWorld& w, const HmpEquisam
 }
 
 struct CtrlLayout {  // d_ctrl: counters [n][4] u32 | hv_out [n][4] u32 | best_out [n][2] f64 | best of the equisampled sweep [n][2] f64
-	size_t off_counters, off_hv, off_best, off_best2, total;
+	                   // | work ticket of a refinement that runs beside the sweep [n][4] u32
+	size_t off_counters, off_hv, off_best, off_best2, off_counters2, total;
 };
 CtrlLayout ctrl_layout(int n_scenes) {
 	CtrlLayout c;
@@ -609,7 +615,8 @@ CtrlLayout ctrl_layout(int n_scenes) {
 	c.off_best = c.off_hv + (size_t)n_scenes * 4 * sizeof(unsigned int);
 	c.off_best = (c.off_best + 15) / 16 * 16;
 	c.off_best2 = c.off_best + (size_t)n_scenes * 2 * sizeof(double);
-	c.total = c.off_best2 + (size_t)n_scenes * 2 * sizeof(double);
+	c.off_counters2 = c.off_best2 + (size_t)n_scenes * 2 * sizeof(double);
+	c.total = c.off_counters2 + (size_t)n_scenes * 4 * sizeof(unsigned int);
 	return c;
 }
 
@@ -770,10 +777,14 @@ HmpContext* hmp_create(int device_id) {
 	if (const char* e = getenv("HMP_REFINE_MIN_LEADERS")) ctx->refine_min_leaders = std::max(1, std::min(256, atoi(e)));
 	if (const char* e = getenv("HMP_REFINE_ROUNDS")) ctx->refine_rounds = std::max(1, std::min(2, atoi(e)));
 	if (getenv("HMP_REFINE_WINDOW_ONLY")) ctx->refine_window_only = 1;
+	if (getenv("HMP_NO_OVERLAP")) ctx->overlap_refine = 0;
 	if (const char* e = getenv("HMP_SWEEP_LAYOUT")) ctx->sweep_layout = std::max(0, std::min(2, atoi(e)));
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
 	    cudaEventCreate(&ctx->evm) != cudaSuccess || cudaEventCreateWithFlags(&ctx->seeds_event[0], cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->seeds_event[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -819,9 +830,16 @@ void hmp_destroy(HmpContext* ctx) {
 		if (ctx->grid_stage_ev[b]) cudaEventDestroy(ctx->grid_stage_ev[b]);
 	}
 	ctx->h_out.release();
+	ctx->h_small.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->evm) cudaEventDestroy(ctx->evm);
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	if (ctx->stream2) {
+		cudaStreamSynchronize(ctx->stream2);
+		cudaStreamDestroy(ctx->stream2);
+	}
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -993,6 +1011,43 @@ static int resolve_wavefronts(HmpContext* ctx) {
 			CU(cudaStreamSynchronize(ctx->stream));
 		}
 	}
+	return HMP_OK;
+}
+
+// hmp_plan's form of the join: the plan stream waits for the side streams and copies the overflow flags into pinned memory;
+// the host does not wait here (it packs and uploads the world meanwhile, the wave fronts of a cycle take ~0.2 ms) and looks at
+// the flags after the cycle's final synchronisation (finish_wavefront_join). joined = number of pending grids.
+static int join_wavefronts_async(HmpContext* ctx, int* joined) {
+	*joined = 0;
+	int rc = ctx->h_small.ensure(64);
+	if (rc) return rc;
+	int32_t* hw = (int32_t*)ctx->h_small.p;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		hw[g] = 0;
+		if (!ctx->wavefront_pending[g]) continue;
+		CU(cudaStreamWaitEvent(ctx->stream, ctx->wf_done[g], 0));
+		CU(cudaMemcpyAsync(&hw[g], ctx->d_seeds[g].p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		(*joined)++;
+	}
+	return HMP_OK;
+}
+// After the stream has been synchronised: a grid whose frontier queue overflowed (never observed for 200 x 200 windows) is
+// recomputed with the scan kernel; redo = 1 tells the caller that the cycle it just ran read an incomplete grid.
+static int finish_wavefront_join(HmpContext* ctx, int* redo) {
+	*redo = 0;
+	const int32_t* hw = (const int32_t*)ctx->h_small.p;
+	for (int g = 0; g < HMP_NUM_MAPGRIDS; ++g) {
+		if (!ctx->wavefront_pending[g]) continue;
+		ctx->wavefront_pending[g] = false;
+		if (hw[g]) {
+			const size_t n = (size_t)ctx->size_x * ctx->size_y;
+			CU(hmp_dev_launch_wavefront((const uint8_t*)ctx->d_costmaps.p, ctx->size_x, ctx->size_y, (const int*)ctx->d_seeds[g].p + 1,
+			                            ctx->n_seeds[g], (float*)ctx->d_mapgrids.p + (size_t)g * n, ctx->stream));
+			ctx->launches++;
+			*redo = 1;
+		}
+	}
+	if (*redo) CU(cudaStreamSynchronize(ctx->stream));
 	return HMP_OK;
 }
 
@@ -1271,6 +1326,16 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		A.pose_slots = (unsigned int*)ctx->d_poseslots.p;
 		A.pose_n_slots = n_slots;
 	}
+	// Small pools in mode 2 (at most one block-cooperative FP64 wave, e.g. the stock 72 + 30 samples): every candidate is a leader
+	// whatever the FP32 sweep says, so the FP64 rollouts do not depend on it and run BESIDE it on a second stream; the FP32
+	// sweep still supplies the counters and the highest_valid_cost_ records. (K as in the refinement below.)
+	const int k_all = std::max(8, (C + 7) / 8 * 8);
+	const bool overlap = ctx->precise == 2 && NS == 1 && ctx->overlap_refine && !ctx->refine_window_only && ctx->refine_max_leaders <= 0 &&
+	                     k_all + blocks_x + equi_blocks <= ctx->sm_count;
+	if (overlap) {
+		CU(cudaEventRecord(ctx->ev_fork, st));   // inputs of the cycle are on the device (uploads, wave fronts, dilated map)
+		CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+	}
 	CU(hmp_dev_launch_plan(&A, blocks_x, sweep_mode, smem_sweep, st));
 	A.pose_scratch = nullptr;   // the detail / refinement launches derived from A do not use it
 	A.pose_slots = nullptr;
@@ -1314,7 +1379,8 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + NS) * sizeof(int32_t) + 8;   // one round's buffers, 8-byte aligned
 		const size_t r_set = (r_bytes + 15) / 16 * 16;
 		// single-scene plans run a second round (below): a second set of buffers + the first round's threshold
-		const int rounds = (NS == 1 && ctx->refine_rounds >= 2) ? 2 : 1;
+		// (not when round 1 already holds every candidate of the pool, C <= K: nothing is left for a second list)
+		const int rounds = (NS == 1 && ctx->refine_rounds >= 2 && (C > K || ctx->refine_window_only)) ? 2 : 1;
 		if ((rc = ctx->d_refine.ensure(r_set * rounds + 2 * NS * sizeof(double)))) return rc;   // + (threshold, effective window) of round 1
 		double* r_thr = (double*)((unsigned char*)ctx->d_refine.p + r_set * rounds);
 		refine_round = [=, &r_count_dev](int round, const int32_t* active) -> int {
@@ -1328,7 +1394,11 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			int32_t* r_count = r_nposes + nk;
 			// round 1: rank-based (the K lowest FP32 totals); round 2: everything not yet refined whose FP32 total lies within the
 			// window above the REFINED best (at most K, the lowest first)
-			if (round == 0 && !ctx->refine_window_only)
+			const bool beside = overlap && round == 0 && !active;   // first pass of a small pool: see `overlap` above
+			cudaStream_t rs = beside ? ctx->stream2 : st;
+			if (beside)
+				CU(hmp_dev_launch_fill_leaders(r_leaders, K, C, r_count, rs));
+			else if (round == 0 && !ctx->refine_window_only)
 				CU(hmp_dev_launch_collect_topk(A.totals, C, A.best_out, K, ctx->refine_window, r_leaders, r_count, r_thr, NS, active, st));
 			else
 				CU(hmp_dev_launch_collect_leaders(A.totals, C, A.best_out, ctx->refine_window, K, r_leaders, r_count,
@@ -1347,6 +1417,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			Rf.totals = r_totals;
 			Rf.d_nposes = r_nposes;
 			Rf.d_forces = nullptr;
+			if (beside) Rf.counters = (unsigned int*)(ctrl + cl.off_counters2);   // its own work ticket: the sweep is pulling from A.counters
 			// single scene: few candidates, many SMs -> one candidate per BLOCK (block-cooperative instance), as many blocks as
 			// the GPU holds; batches have enough leaders in total to keep one warp per candidate
 			// The block-cooperative instance finishes a wave of <= sm_count leaders in ~0.85 ms (cfg2), the warp-per-candidate
@@ -1354,7 +1425,11 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			// the previous cycle's count (consecutive control cycles have similar leader sets). The second round's list is
 			// almost always empty (its blocks find no candidate and leave): one warp per candidate, two per block.
 			if (NS == 1 && round == 0 && K <= ctx->sm_count) {
-				CU(hmp_dev_launch_plan(&Rf, K, 3, smem, st));   // a small pool: one block-cooperative FP64 rollout per SM
+				CU(hmp_dev_launch_plan(&Rf, K, 3, smem, rs));   // a small pool: one block-cooperative FP64 rollout per SM
+				if (beside) {
+					CU(cudaEventRecord(ctx->ev_join, rs));
+					CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+				}
 			} else if (NS == 1) {
 				// one wave: every SM takes ceil(K / SMs) candidates, one per warp (round 2 is almost always empty: its blocks leave)
 				const int wpt = std::max(1, std::min(HMP_WARPS_PER_BLOCK, (K + ctx->sm_count - 1) / ctx->sm_count));
@@ -1382,8 +1457,13 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			CU(cudaMemsetAsync(ctrl + cl.off_counters, 0, (size_t)NS * 4 * sizeof(unsigned int), st));
 			if ((rc = refine_round(1, nullptr))) return rc;
 		}
-		CU(cudaMemcpyAsync(&ctx->last_n_leaders, r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-		if (r_count_dev[1]) CU(cudaMemcpyAsync(&ctx->last_n_leaders2, r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		// leader counts: into pinned words (a copy to pageable memory would block the host until the stream has drained, i.e.
+		// before the hv pass and the result copies are even queued); picked up after the final synchronisation
+		if ((rc = ctx->h_small.ensure(64))) return rc;
+		int32_t* hw = (int32_t*)ctx->h_small.p;
+		hw[4] = hw[5] = 0;
+		CU(cudaMemcpyAsync(&hw[4], r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		if (r_count_dev[1]) CU(cudaMemcpyAsync(&hw[5], r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
 	// highest_valid_cost_ of the MapGrid critics as the reference's sequential, early-exiting loop would leave it: needs the final
 	// explored totals (refined leaders included) for the best-so-far every candidate was scored against
@@ -1405,6 +1485,10 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		return HMP_OK;
 	};
 	if ((rc = read_back())) return rc;
+	if (ctx->precise == 2) {
+		ctx->last_n_leaders = ((const int32_t*)ctx->h_small.p)[4];
+		ctx->last_n_leaders2 = ((const int32_t*)ctx->h_small.p)[5];
+	}
 	float ms = 0.f;
 	CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	float ms_main = 0.f;
@@ -1526,7 +1610,7 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 		return HMP_E_NOT_READY;
 	}
 	CU(cudaSetDevice(ctx->device));
-	if ((rc = resolve_wavefronts(ctx))) return rc;
+	if (ctx->batch_wf_pending && (rc = resolve_wavefronts(ctx))) return rc;
 	int T = compute_steps(ctx->params.general, std::hypot(world->vel_x, world->vel_y), world->vel_th);
 	if (T < 1 || T > HMP_MAX_STEPS) {
 		set_err("rollout has %d steps, supported 1..%d", T, HMP_MAX_STEPS);
@@ -1549,9 +1633,19 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 	}
 	pack_scene(ctx, *world, ctx->hv_prev, D.dt_d, (unsigned char*)ctx->h_stage.p, D.n_equi);
 	uint32_t used = reinterpret_cast<DevScene*>(ctx->h_stage.p)->blob_bytes;
+	// device wave fronts of this cycle (hmp_compute_mapgrid) have been running on their side streams while the host packed the
+	// world; the plan stream joins them here, their overflow flags are read with the cycle's final synchronisation
+	int joined = 0;
+	if ((rc = join_wavefronts_async(ctx, &joined))) return rc;
 	CU(cudaMemcpyAsync(ctx->d_scenes.p, ctx->h_stage.p, used, cudaMemcpyHostToDevice, ctx->stream));
 	PlanLaunch pl{1, used, n_extra, T};
-	return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
+	if ((rc = run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity))) return rc;
+	if (joined) {
+		int redo = 0;
+		if ((rc = finish_wavefront_join(ctx, &redo))) return rc;
+		if (redo) return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
+	}
+	return HMP_OK;
 }
 
 // Uploads the per-scene costmaps of a batch (scene s = cells + s * size_x * size_y) into the padded device layout.
