@@ -32,7 +32,9 @@ extern "C" size_t hmp_dev_smem_bytes(uint32_t scene_stride, uint32_t costmap_str
 extern "C" cudaError_t hmp_dev_configure(size_t max_smem);
 extern "C" cudaError_t hmp_dev_occupancy(size_t smem, int precise, int* blocks_per_sm);
 extern "C" cudaError_t hmp_dev_occupancy_tpc(size_t smem, int threads, int rich, int* blocks_per_sm);
+extern "C" cudaError_t hmp_dev_occupancy_tpc64(size_t smem, int threads, int* blocks_per_sm);
 extern "C" int hmp_dev_tpc_max_threads();
+extern "C" int hmp_dev_tpc64_max_threads();
 extern "C" size_t hmp_dev_tpc_extra_smem(uint32_t scene_stride);
 extern "C" cudaError_t hmp_dev_launch_plan(const KernelArgs* args, int blocks_x, int detail, size_t smem, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_env_filter(const HmpShape* shapes, int n_shapes, const double* verts, const HmpPerson* people, int n_people,
@@ -661,8 +663,11 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 	// Layout of the FP32 sweep. One warp per candidate (plan_kernel) has the shortest latency for a few thousand
 	// candidates; one thread per candidate (sweep_tpc_kernel) issues the per-step scalar section once per 32 candidates
 	// and wins as soon as the launch holds enough candidates to give every SM sub-partition a warp.
+	// The exact-parity sweep (precision mode 1) has the same two layouts; its thread-per-candidate instance is compiled for one
+	// block per SM (225 registers, no spills). HMP_F64_WARP=1 keeps the warp-per-candidate FP64 sweep (A/B).
 	int tpc_threads = 0;
-	if (sweep_mode_out && ctx->precise != 1) {
+	const bool f64 = ctx->precise == 1;
+	if (sweep_mode_out && !(f64 && getenv("HMP_F64_WARP"))) {
 		const long long total = (long long)C * pl.n_scenes;
 		const bool want = ctx->sweep_layout == 2 || (ctx->sweep_layout == 0 && total >= 16384);
 		if (want) {
@@ -671,6 +676,13 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 			while (tpc_threads > 64 && ((long long)C + tpc_threads - 1) / tpc_threads * pl.n_scenes * 10 < (long long)ctx->sm_count * 9)
 				tpc_threads = (tpc_threads > 128) ? 128 : 64;
 		}
+	}
+	if (tpc_threads && f64) {
+		// finer tickets balance the two rounds a 64k grid takes at 8 warps per SM (rejected candidates end early)
+		const char* e = getenv("HMP_F64_TPC_THREADS");
+		const int v = e ? atoi(e) : hmp_dev_tpc64_max_threads();
+		tpc_threads = std::min(tpc_threads, hmp_dev_tpc64_max_threads());
+		if (v >= 32 && v <= hmp_dev_tpc64_max_threads() && v % 32 == 0) tpc_threads = std::min(tpc_threads, v);
 	}
 	size_t smem_sweep = smem;
 	ctx->tpc_defer = 0;
@@ -689,20 +701,23 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 		int b0 = 0, b1 = 0;
 		const long long warps = (((long long)C + tpc_threads - 1) / tpc_threads) * pl.n_scenes * (tpc_threads / 32);
 		const int rich = (warps <= (long long)ctx->sm_count * 8 && !getenv("HMP_TPC_NO_RICH")) ? 1 : 0;
-		if (with <= ctx->max_smem_optin && hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, rich, &b0) == cudaSuccess &&
-		    hmp_dev_occupancy_tpc(with, tpc_threads, rich, &b1) == cudaSuccess && b1 >= b0 && b1 >= 1) {
+		auto occ = [&](size_t bytes, int* b) {
+			return f64 ? hmp_dev_occupancy_tpc64(bytes, tpc_threads, b) : hmp_dev_occupancy_tpc(bytes, tpc_threads, rich, b);
+		};
+		if (with <= ctx->max_smem_optin && occ(smem_sweep, &b0) == cudaSuccess && occ(with, &b1) == cudaSuccess && b1 >= b0 && b1 >= 1) {
 			smem_sweep = with;
 			ctx->tpc_defer = 1;
 		}
 	}
 	// few warps per SM sub-partition anyway (<= 2): the register-rich instance of the thread-per-candidate sweep
 	int tpc_rich = 0;
-	if (tpc_threads) {
+	if (tpc_threads && !f64) {
 		const long long warps = (((long long)C + tpc_threads - 1) / tpc_threads) * pl.n_scenes * (tpc_threads / 32);
 		tpc_rich = (warps <= (long long)ctx->sm_count * 8 && !getenv("HMP_TPC_NO_RICH")) ? 1 : 0;
 	}
 	int bps = 0;
-	if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, tpc_rich, &bps));
+	if (tpc_threads && f64) CU(hmp_dev_occupancy_tpc64(smem_sweep, tpc_threads, &bps));
+	else if (tpc_threads) CU(hmp_dev_occupancy_tpc(smem_sweep, tpc_threads, tpc_rich, &bps));
 	if (tpc_threads) ctx->tpc_bps = bps;
 	else CU(hmp_dev_occupancy(smem, ctx->precise == 1, &bps));
 	if (bps < 1) {
@@ -1545,6 +1560,13 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		r.n_generated = (int)h_counters[4 * s + 2];
 		r.n_valid = (int)h_counters[4 * s + 3];
 		r.best_total = best >= 0 ? h_best[2 * s] : -7.0;  // caller pre-sets cost_ = -7, humap_planner.cpp:1364
+		if (best >= 0 && ctx->precise == 1 && sweep_mode) {
+			// exact mode through the thread-per-candidate sweep: its FP32 critics are evaluated in another (equivalent) form than the
+			// winner's detail pass, 1e-8 relative apart. The published total is the detail pass's -- the number that goes with the
+			// published critics, and the one mode 2 reports for the same candidate.
+			const double det_total = (h_det + (size_t)NS * (HMP_NUM_COSTS + 3 + (size_t)T * 3))[s];
+			if (det_total >= 0.0) r.best_total = det_total;
+		}
 		r.time_delta = D.dt_d;
 		r.gpu_ms = ms;
 		r.gpu_ms_select = ms_main;

@@ -207,23 +207,42 @@ __device__ __noinline__ StaticSum static_loop_packed(const float4* __restrict__ 
 #ifndef HMP_TPC_MIN_BLOCKS
 #define HMP_TPC_MIN_BLOCKS (512 / HMP_TPC_THREADS)
 #endif
+// launch bounds of the FP64 instance (exact-parity mode): largest block and resident blocks per SM the registers are budgeted for
+#ifndef HMP_F64_TPC_MAXTHREADS
+#define HMP_F64_TPC_MAXTHREADS HMP_TPC_THREADS
+#endif
+// Two blocks of 256 threads per SM (128 registers, some spill) so that a 64k-candidate grid is ONE wave of 2048 warps on 2368
+// slots: 36.4 ms (cfg2 seed 0) against 43.0 ms for the spill-free 225-register build, which holds 8 warps per SM and needs two
+// rounds; 168 registers / 12 warps per SM: 52 ms (still two rounds). One static object in flight (two: 38.3 ms, four: 48 ms).
+#ifndef HMP_F64_TPC_MINB
+#define HMP_F64_TPC_MINB 2
+#endif
+#ifndef HMP_F64_TPC_UNROLL
+#define HMP_F64_TPC_UNROLL 1   /* static objects in flight per thread of the FP64 instance */
+#endif
 // MINB = resident blocks per SM the registers are budgeted for: 2 (128 registers, 16 warps per SM) for launches that fill the
 // GPU, 1 (up to 255 registers: the kernel takes ~200 and loses its spills) for launches that leave at most two warps per SM
 // sub-partition anyway -- there a warp's speed is pure latency and the extra registers are free (cfg1: sweep 1.59 -> 1.52 ms).
 // DEFER: the instance with the deferred obstacle critic (launched when KernelArgs.pose_scratch is set); the other instance is
 // compiled without that code (its register pressure costs the few-object batched worlds of config 4 a quarter of their speed).
+// RT = double: the exact-parity sweep (hmp_set_precision 1) in this layout -- object loops, FIS and the per-step scalar section in
+// FP64 with the literal formulations of plan_kernel<false, double> (no packed loop, no float copies of the records); the critics
+// stay FP32 on the FP64 poses as in every instance. A lane evaluates ONE candidate: no shuffle reductions, the scalar section
+// once per candidate instead of 32 times per warp, and the 32 lanes of a warp meet the SAME object in the divergent literal
+// FIS, from neighbouring candidates (similar geometry) instead of 32 different objects.
 #ifdef HMP_TPC_MAXNREG
-template <int MINB, bool DEFER>
+template <int MINB, bool DEFER, typename RT = float>
 __global__ void __maxnreg__(HMP_TPC_MAXNREG) sweep_tpc_kernel(const KernelArgs A) {
 #else
-template <int MINB, bool DEFER>
-__global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const KernelArgs A) {
+template <int MINB, bool DEFER, typename RT = float>
+__global__ void __launch_bounds__(sizeof(RT) == 8 ? HMP_F64_TPC_MAXTHREADS : HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const KernelArgs A) {
 #endif
-	using R = float;
-	using SC = float;
-	using TwistS = TwistT<float>;
+	using R = RT;
+	using SC = RT;
+	using TwistS = TwistT<RT>;
+	constexpr bool F32 = (sizeof(RT) == 4);
 	constexpr int NW = HMP_TPC_THREADS / 32;
-	constexpr int TPC_UNROLL = HMP_TPC_UNROLL;   // static objects in flight per thread
+	constexpr int TPC_UNROLL = (sizeof(RT) == 8) ? HMP_F64_TPC_UNROLL : HMP_TPC_UNROLL;   // static objects in flight per thread
 	[[maybe_unused]] constexpr int TPC_PAIR_UNROLL = HMP_TPC_PAIR_UNROLL;
 	constexpr int TPC_DYN_UNROLL = HMP_TPC_DYN_UNROLL, TPC_PPL_UNROLL = HMP_TPC_PPL_UNROLL;   // dynamic objects / people in flight per thread   // ... pairs of them in the packed loop
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -293,8 +312,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 	// Static objects once more, as pairs of hi / lo floats (o = hi + lo to 2^-48): pair p = objects 2p, 2p + 1 as
 	// {xh0, xh1, yh0, yh1} {xl0, xl1, yl0, yl1}, so that one 16-byte broadcast load feeds the packed arithmetic of two objects
 	// and the difference to the robot position needs no FP64 subtraction and no conversion
-	const float4* pairs = reinterpret_cast<const float4*>(smem + ((L.total + 15u) & ~15u));
-	{
+	[[maybe_unused]] const float4* pairs = reinterpret_cast<const float4*>(smem + ((L.total + 15u) & ~15u));
+	if constexpr (F32) {
 		float* pf = reinterpret_cast<float*>(smem + ((L.total + 15u) & ~15u));
 		const int nsm = max(S.n_static0, S.n_static);
 		for (int j = tid; j < nsm; j += blockDim.x) {
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 	// Dynamic objects: dir_beta and speed are only ever read as floats, the velocity as both: their float copies
 	// {dir_beta, speed, vx, vy} go over the last 16 bytes of the record (the double `speed` and the padding), saving four
 	// conversions per object-step
-	for (int k = tid; k < max(S.n_dynamic, S.n_dynamic_later); k += blockDim.x) {
+	for (int k = tid; F32 && k < max(S.n_dynamic, S.n_dynamic_later); k += blockDim.x) {
 		const DevDynamic o = dynamics[k];
 		float4* w = reinterpret_cast<float4*>(const_cast<DevDynamic*>(dynamics + k)) + 3;
 		*w = make_float4((float)o.dir_beta, (float)o.speed, (float)o.vx, (float)o.vy);
@@ -413,7 +432,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 		const int cand = active ? wk + A.cand_offset : 0;
 
 		// ---- SampleAmplifierSet of this candidate (social_trajectory_generator.cpp:166-217) ----------
-		float v_des, An, Bn, Cn, Ap, Bp, Cp, Aw, Bw, As;
+		float v_des, An, Bn, Cn, Ap, Bp, Cp, Aw, Bw;
+		R As;   // :641: the human-action amplifier is not truncated to float; the FP32 instance rounds it
 		{
 			double amp[HMP_NUM_AMPLIFIERS];
 			if (cand < P.n_grid) {
@@ -441,14 +461,14 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			Cp = (float)((double)P.base[6] * amp[HMP_AMP_CP]);
 			Aw = (float)((double)P.base[7] * amp[HMP_AMP_AW]);
 			Bw = (float)((double)P.base[8] * amp[HMP_AMP_BW]);
-			As = (float)amp[HMP_AMP_AS];
+			As = (R)amp[HMP_AMP_AS];
 		}
 
 		// ---- rollout state (per thread = per candidate) ------------------------------------------------
 		double x = S.x0, y = S.y0, th = S.yaw0;   // the pose is FP64 in every instance
 		SC ux = (SC)S.u0x_d, uy = (SC)S.u0y_d, uw = (SC)S.u0w_d;
 		bool rejected = false;
-		float seed_x = 0.f, seed_w = 0.f;
+		SC seed_x = 0, seed_w = 0;
 		bool ob_neg = false;
 		int ob_best = 0;
 		int ob_lb = 0;   // deferred critic: largest centre-cell cost so far, a lower bound of the final maximum
@@ -464,15 +484,15 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 		int un_n = 0;
 		float hcs = 0.f, vsm_x = 0.f, vsm_y = 0.f;
 		TwistS prev_tw = {0, 0, 0};
-		float last_tgx = 0.f, last_tgy = 0.f;  // global velocity of the last wrapped-Trajectory velocity (TTC look-ahead)
+		SC last_tgx = 0, last_tgy = 0;  // global velocity of the last wrapped-Trajectory velocity (TTC look-ahead)
 
 		const bool forces_on = !P.disable_interaction;
 		const R fovh = (R)P.fov_half_d, fovg = (R)P.fov_gauss_scale_d, fovn = (R)P.fov_neg_inv_2var_d;
-		const R neg_inv_Bw = -1.0f / Bw;
-		const R nbw_l2 = neg_inv_Bw * 1.4426950408889634f, fovn_l2 = fovn * 1.4426950408889634f;
-		const R aw_g = Aw * fovg;
-		constexpr R L2E = 1.4426950408889634f;
-		const R nBn_l2 = -Bn * L2E, Cn_l2 = Cn * L2E, nBp_l2 = -Bp * L2E, Cp_l2 = Cp * L2E;
+		const R neg_inv_Bw = (R)-1 / (R)Bw;
+		[[maybe_unused]] const R nbw_l2 = neg_inv_Bw * (R)1.4426950408889634, fovn_l2 = fovn * (R)1.4426950408889634;
+		[[maybe_unused]] const R aw_g = (R)Aw * fovg;
+		constexpr R L2E = (R)1.4426950408889634;
+		[[maybe_unused]] const R nBn_l2 = -(R)Bn * L2E, Cn_l2 = (R)Cn * L2E, nBp_l2 = -(R)Bp * L2E, Cp_l2 = (R)Cp * L2E;
 
 		for (int i = 0; i < T; ++i) {
 			bool alive = active && !rejected;
@@ -488,7 +508,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			if (alive) {
 				sincos(th, &sd, &cd);
 				const double rxd = x - S.x0, ryd = y - S.y0;
-				const float dpsi_f = (float)(th - S.yaw0);
+				[[maybe_unused]] const float dpsi_f = (float)(th - S.yaw0);
+				[[maybe_unused]] const double dpsi = th - S.yaw0;
 				const double tnow = (double)i * P.dt_d;
 				// -- derived robot data (world.cpp:20-33) --
 				const SC speed_d = sqrt_s(ux * ux + uy * uy);
@@ -499,8 +520,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 					SC dx = (SC)(S.glx_d - rxd), dy = (SC)(S.gly_d - ryd);
 					SC dl = sqrt_s(dx * dx + dy * dy);
 					SC inv = (dl <= (SC)1e-6) ? (SC)1 : (SC)1 / dl;
-					fix = (SC)P.m_over_tau * (v_des * (dx * inv) - ux);
-					fiy = (SC)P.m_over_tau * (v_des * (dy * inv) - uy);
+					fix = (SC)P.m_over_tau * ((SC)v_des * (dx * inv) - ux);
+					fiy = (SC)P.m_over_tau * ((SC)v_des * (dy * inv) - uy);
 				}
 				const SC gdx = (SC)(S.gx_d - rxd), gdy = (SC)(S.gy_d - ryd);
 				const SC goal_dist = sqrt_s(gdx * gdx + gdy * gdy);
@@ -519,34 +540,37 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 						R dx = (R)(o.x - rxd), dy = (R)(o.y - ryd);
 						R dist, ia;
 						len_inv(dx * dx + dy * dy, dist, ia);
-						dmin = fminf(dmin, dist);
+						dmin = fminf(dmin, (float)dist);
 						R bx = -dx - yx, by = -dy - yy;
 						R bl, ib;
 						len_inv(bx * bx + by * by, bl, ib);
 						R sum = dist + bl;
 						R w = (R)0.5 * sqrt_nr(sum * sum - yl2);
-						const bool valid = forces_on && (fabsf(w) >= (R)1e-8) && !(dist < (R)1e-8);  // false for NaN too
+						const bool valid = forces_on && (fabs(w) >= (R)1e-8) && !(dist < (R)1e-8);  // false for NaN too
 						if (dist <= (R)1e-6) ia = (R)1;   // ignition Vector3::Normalize leaves near-zero vectors unscaled
 						if (bl <= (R)1e-6) ib = (R)1;
 						R ex = -dx * ia + bx * ib, ey = -dy * ia + by * ib;
-						R arel = wrapf(atan2_r(dy, dx) - heading_r);
+						R arel = wrap_r(atan2_r(dy, dx) - heading_r);
 						R gmag;
-						if constexpr (GAUSS) {
+						if constexpr (F32 && GAUSS) {
 							// Aw e^{-w/Bw} * g e^{-a^2 / (2 sigma^2)} with ONE exponential: both exponents pre-scaled by log2(e)
 							gmag = aw_g * ex2_ftz(fmaf(w, nbw_l2, arel * arel * fovn_l2)) * (sum * w) * (R)0.25;
+						} else if constexpr (!F32 && GAUSS && HMP_F64_FAST) {
+							// the FP64 form of plan_kernel<false, double>: one exp instead of two
+							gmag = ((R)Aw * fovg) * exp_r(fma(w, neg_inv_Bw, arel * arel * fovn)) * ((sum * (R)0.5) * w) * (R)0.5;
 						} else {
-							gmag = Aw * expf(w * neg_inv_Bw) * ((sum / (R)2) * w) * (R)0.5;
-							gmag *= fov_factor<R>(arel, 1, fovh, fovg, fovn);
+							gmag = (R)Aw * exp_r(w * neg_inv_Bw) * ((sum / (R)2) * w) * (R)0.5;
+							gmag *= fov_factor<R>(arel, GAUSS ? 0 : 1, fovh, fovg, fovn);
 						}
 						gmag = valid ? gmag : (R)0;
-						fsx = fmaf(gmag, ex, fsx);
-						fsy = fmaf(gmag, ey, fsy);
+						fsx = fma(gmag, ex, fsx);
+						fsy = fma(gmag, ey, fsy);
 					};
 					if (P.fov_method == 0) {
 						int j0 = 0;
 #if HMP_TPC_PACKED
 #if HMP_TPC_STATIC_CALL
-						if (forces_on) {
+						if constexpr (F32) if (forces_on) {
 							const int npairs = ns >> 1;
 							const float rxh = (float)rxd, ryh = (float)ryd;
 							const bool moving = !(speed_d <= (SC)0.01);
@@ -561,7 +585,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 							}
 						}
 #else
-						if (forces_on) {
+						if constexpr (F32) if (forces_on) {
 							// ---- two objects per iteration in packed FP32x2 arithmetic; same formulas as static_body ----
 							const int npairs = ns >> 1;
 							const float rxh = (float)rxd, ryh = (float)ryd;
@@ -635,6 +659,50 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 					const int nd = (i == 0) ? S.n_dynamic : S.n_dynamic_later;
 					const R nine = (R)9 * Cst<R>::deg();
 					const R speed_r = speed_d;
+					if constexpr (!F32) {
+						// FP64: the literal loop of plan_kernel<false, double> (double records, IEEE-class routines, literal FIS)
+#pragma unroll 1
+						for (int k = 0; k < nd; ++k) {
+							const DevDynamic& o = dynamics[k];
+							R dx = (R)(fma(tnow, o.vx, o.d0x) - rxd), dy = (R)(fma(tnow, o.vy, o.d0y) - ryd);
+							R dist = sqrt_nr(dx * dx + dy * dy);
+							dmin = fminf(dmin, (float)dist);
+							if (!forces_on) continue;
+							R angle_d = atan2_r(dy, dx);
+							R rel = angle_d - (R)wrapd(o.psi0 + dpsi);
+							R arel = fabs(rel);
+							R side = (arel <= nine || arel >= Cst<R>::pi() - nine) ? (R)0 : ((rel <= (R)0) ? (R)-1 : (R)1);
+							R rel_loc = wrap_r(rel);
+							if (dist <= (R)7.5) {
+								R vrx = (R)o.vx - (R)ux, vry = (R)o.vy - (R)uy;
+								R vrel = sqrt_nr(vrx * vrx + vry * vry);
+								if (vrel >= (R)1e-6) {
+									R fov = fov_factor<R>(rel_loc, P.fov_method, fovh, fovg, fovn);
+									R thab = wrap_r(th_r - angle_d);
+									R en = (R)An * exp_r(div_r(-(R)Bn * thab * thab, vrel) - (R)Cn * dist) * fov;
+									R ep = (R)Ap * exp_r(div_r(-(R)Bp * fabs(thab), vrel) - (R)Cp * dist) * fov * side;
+									fdx_r += c_r * en + s_r * ep;
+									fdy_r += s_r * en - c_r * ep;
+								}
+							}
+							if (P.fis_on && dist <= (R)P.fis_range_d) {
+								R strength = (exp_r(speed_r + (R)o.speed) - (R)1) * exp_r(-dist);
+								R val, mu;
+								fis_process<R>(heading_r, (R)o.dir_beta, rel_loc, angle_d, val, mu);
+								if (mu > (R)0) {
+									R ff = (R)1;
+									if (P.fis_fov_method == 0 || P.fis_fov_method == 1)
+										ff = fov_factor<R>(rel_loc, P.fis_fov_method, (R)P.fis_fov_half_d, (R)P.fis_gauss_scale_d,
+										                   (R)P.fis_neg_inv_2var_d);
+									R mag = As * mu * strength * ff;
+									R sv, cv;
+									sincos_r(val, &sv, &cv);
+									fhx = fma(mag, cv, fhx);
+									fhy = fma(mag, sv, fhy);
+								}
+							}
+						}
+					} else {
 #pragma unroll TPC_DYN_UNROLL
 					for (int k = 0; k < nd; ++k) {
 						const DevDynamic& o = dynamics[k];
@@ -684,6 +752,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 							}
 						}
 					}
+					}   // F32
 				}
 				// TTC: first world index whose running minimum distance is within the collision distance
 				// (ttc_cost_function.cpp:72-82)
@@ -712,7 +781,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 						SC k = (SC)P.max_force / mag;
 						fix *= k; fiy *= k; fdx *= k; fdy *= k; Fsx *= k; Fsy *= k;
 					} else if (mag <= (SC)P.min_force) {
-						SC ext = fabsf(mag - (SC)P.min_force);
+						SC ext = fabs(mag - (SC)P.min_force);
 						SC inv = (mag <= (SC)1e-6) ? (SC)1 : (SC)1 / mag;
 						fdx += ext * cx * inv;
 						fdy += ext * cy * inv;
@@ -720,13 +789,18 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				}
 				// -- computeTwist (transformations.cpp:61-126) --
 				const SC Fx = fix + fdx + Fsx + Fhx, Fy = fiy + fdy + Fsy + Fhy;
-				const bool has_force = !((Fx * Fx + Fy * Fy) <= 1e-16f);   // |F| <= 1e-8 without the sqrt
+				bool has_force;
+				if constexpr (F32) has_force = !((Fx * Fx + Fy * Fy) <= 1e-16f);   // |F| <= 1e-8 without the sqrt
+				else has_force = !(sqrt(Fx * Fx + Fy * Fy) <= 1e-8);
 				if (has_force && !(P.mass <= 1e-6)) {
 					SC ax = Fx / (SC)P.mass, ay = Fy / (SC)P.mass;
 					SC vv = cs * ax + ss * ay;
 					const SC vcross = -ss * ax + cs * ay;
 					// angle of the force relative to the yaw: polynomial atan2 of (F . e_yaw, F x e_yaw), no wrap needed
-					SC ang = atan2_r(vcross, vv);
+					// (the FP64 instance keeps the literal form Angle(atan2(Fy, Fx) - yaw), normalised)
+					SC ang;
+					if constexpr (F32) ang = atan2_r(vcross, vv);
+					else ang = wrapd(atan2_r(Fy, Fx) - th);
 					SC vw = vcross + (SC)P.rot_comp * ang;
 					tw = saturate_velocity<SC>({vv, 0, vw}, (SC)P.max_vel_x, (SC)0, (SC)P.max_vel_x, (SC)P.max_vel_theta, (SC)P.back_max);
 				}
@@ -735,7 +809,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 					TwistS vl = {ux * cs + uy * ss, 0, uw};  // computeVelocityLocal, non-holonomic
 					SC smax = sqrt_s((SC)2 * (SC)P.acc_decel * goal_dist);
 					SC ca = 1, sa = 0;
-					if (fabsf(vl.x) >= (SC)1e-4 || fabsf(vl.y) >= (SC)1e-4) {
+					if (fabs(vl.x) >= (SC)1e-4 || fabs(vl.y) >= (SC)1e-4) {
 						// cos / sin of atan2(cmd.y, cmd.x) without the trigonometry (atan2(0, 0) = 0 -> (1, 0))
 						SC tl = sqrt_s(tw.x * tw.x + tw.y * tw.y);
 						if (tl > (SC)0) {
@@ -746,15 +820,15 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 						}
 					}
 					const SC adt_x = (SC)P.acc_x * (SC)P.dt_d, adt_y = (SC)P.acc_y * (SC)P.dt_d, adt_w = (SC)P.acc_th * (SC)P.dt_d;
-					SC max_x = fmaxf(fminf((SC)P.max_vel_x, ca * smax), (SC)P.min_vel_x);
-					SC max_y = fmaxf(fminf((SC)P.max_vel_y, sa * smax), (SC)P.min_vel_y);
-					SC lo_x = fmaxf((SC)P.min_vel_x, vl.x - adt_x), hi_x = fminf(max_x, vl.x + adt_x);
-					SC lo_y = fmaxf((SC)P.min_vel_y, vl.y - adt_y), hi_y = fminf(max_y, vl.y + adt_y);
-					SC lo_w = fmaxf(-(SC)P.max_vel_theta, vl.w - adt_w), hi_w = fminf((SC)P.max_vel_theta, vl.w + adt_w);
+					SC max_x = fmax(fmin((SC)P.max_vel_x, ca * smax), (SC)P.min_vel_x);
+					SC max_y = fmax(fmin((SC)P.max_vel_y, sa * smax), (SC)P.min_vel_y);
+					SC lo_x = fmax((SC)P.min_vel_x, vl.x - adt_x), hi_x = fmin(max_x, vl.x + adt_x);
+					SC lo_y = fmax((SC)P.min_vel_y, vl.y - adt_y), hi_y = fmin(max_y, vl.y + adt_y);
+					SC lo_w = fmax(-(SC)P.max_vel_theta, vl.w - adt_w), hi_w = fmin((SC)P.max_vel_theta, vl.w + adt_w);
 					if (!P.maintain_rate) {
-						tw.x = fminf(fmaxf(lo_x, tw.x), hi_x);
-						tw.y = fminf(fmaxf(lo_y, tw.y), hi_y);
-						tw.w = fminf(fmaxf(lo_w, tw.w), hi_w);
+						tw.x = fmin(fmax(lo_x, tw.x), hi_x);
+						tw.y = fmin(fmax(lo_y, tw.y), hi_y);
+						tw.w = fmin(fmax(lo_w, tw.w), hi_w);
 					} else {
 						tw = adjust_proportional<SC>(vl, tw, lo_x, lo_y, lo_w, hi_x, hi_y, hi_w);
 					}
@@ -763,7 +837,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				{
 					SC sl = sqrt_s(tw.x * tw.x + tw.y * tw.y);
 					bool trans_wrong = (P.min_vel_trans >= 0.0) && ((sl + (SC)1e-4) < (SC)P.min_vel_trans);
-					bool theta_wrong = (P.min_vel_theta >= 0.0) && ((fabsf(tw.w) + (SC)1e-4) < (SC)P.min_vel_theta);
+					bool theta_wrong = (P.min_vel_theta >= 0.0) && ((fabs(tw.w) + (SC)1e-4) < (SC)P.min_vel_theta);
 					if ((trans_wrong && theta_wrong) || ((P.max_vel_trans >= 0.0) && ((sl - (SC)1e-4) > (SC)P.max_vel_trans))) {
 						rejected = true;
 						alive = false;
@@ -875,22 +949,25 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 				if (i < n_vel) {
 					last_tgx = tgx_d;
 					last_tgy = tgy_d;
+					// the critics are FP32 on float copies of the twist in every instance (as in plan_kernel)
+					const float twx = (float)tw.x, twy = (float)tw.y, tww = (float)tw.w;
+					const float tgx = (float)tgx_d, tgy = (float)tgy_d;
 					// UnsaturatedTranslationCostFunction (:31-87)
 					if (i == 0 || P.unsat_whole) {
-						un_x += fabsf(tw.x - P.unsat_max_x);
-						un_y += fabsf(tw.y - P.unsat_max_y);
-						un_xy += fabsf(hypotf(tw.x, tw.y) - P.unsat_max_trans);
+						un_x += fabsf(twx - P.unsat_max_x);
+						un_y += fabsf(twy - P.unsat_max_y);
+						un_xy += fabsf(hypotf(twx, twy) - P.unsat_max_trans);
 						un_n++;
 					}
 					// HeadingChangeSmoothness (:15-43), VelocitySmoothness (:18-50)
 					if (i == 0) {
-						hcs = fabsf(tw.w - S.vlw);
-						vsm_x = fabsf(tw.x - S.vlx);
-						vsm_y = fabsf(tw.y - S.vly);
+						hcs = fabsf(tww - S.vlw);
+						vsm_x = fabsf(twx - S.vlx);
+						vsm_y = fabsf(twy - S.vly);
 					} else {
-						hcs += fabsf(tw.w - prev_tw.w) / dt;
-						vsm_x += fabsf(tw.x - prev_tw.x);
-						vsm_y += fabsf(tw.y - prev_tw.y);
+						hcs += (float)fabs(tw.w - prev_tw.w) / dt;
+						vsm_x += (float)fabs(tw.x - prev_tw.x);
+						vsm_y += (float)fabs(tw.y - prev_tw.y);
 					}
 					prev_tw = tw;
 					// people critics: heading disturbance, personal space, passing speed
@@ -899,8 +976,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 					const bool do_ps = (i == 0 || P.ps_whole) && P.scale[HMP_COST_PASSING_SPEED] != 0.0;
 					if (!dead && (do_hd || do_psi || do_ps)) {
 						const float tp = (float)i * P.people_dt;
-						const float rspeed = hypotf(tgx_d, tgy_d);
-						const float motion_dir = atan2_r(tgy_d, tgx_d);
+						const float rspeed = hypotf(tgx, tgy);
+						const float motion_dir = atan2_r(tgy, tgx);
 						const float sp_norm = fminf(fmaxf(rspeed * P.ps_inv_max_speed, 0.0f), 1.0f);
 						if (people_tab) {
 							// table path (all yaw rates zero). The heading-disturbance critic needs two angles only as squares: the
@@ -909,7 +986,7 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 							// packed evaluation, instead of two atan2 and three wraps
 							const bool hd_ok = do_hd && !(rspeed < 1e-9f);
 							const float inv_rs = hd_ok ? 1.0f / rspeed : 0.0f;
-							const float mxu = tgx_d * inv_rs, myu = tgy_d * inv_rs;   // unit motion direction
+							const float mxu = tgx * inv_rs, myu = tgy * inv_rs;   // unit motion direction
 							const float hd_speed = rspeed * P.hd_inv_max_speed;
 							const float4* pt = reinterpret_cast<const float4*>(people);
 #pragma unroll TPC_PPL_UNROLL
@@ -1074,8 +1151,8 @@ __global__ void __launch_bounds__(HMP_TPC_THREADS, MINB) sweep_tpc_kernel(const 
 			}
 			raw[HMP_COST_UNSATURATED] = (un_n > 0) ? (double)(fmaxf(fmaxf(un_x, un_y), un_xy) / (float)un_n) : 0.0;
 			// PreferForwardCostFunction
-			raw[HMP_COST_BACKWARD] = (seed_x < 0.0 || (seed_x < 0.1 && fabsf(seed_w) < 0.2)) ? (double)P.backward_penalty
-			                                                                                 : (double)(fabsf(seed_w) * 10);
+			raw[HMP_COST_BACKWARD] = (seed_x < 0.0 || (seed_x < 0.1 && fabs(seed_w) < 0.2)) ? (double)P.backward_penalty
+			                                                                                : (double)(fabs(seed_w) * 10);
 			{
 				double c = 0.0;
 				if (ttc_first != 0x7fffffff) {
