@@ -560,7 +560,7 @@ def main():
         except Exception:
             instrumented = None
         mode = pl.last_sweep_mode()
-        sweep_name = (f"sweep_tpc_kernel (one thread per candidate, {mode} threads per block)" if mode
+        sweep_name = (f"sweep_tpc_kernel{'<double>' if int(args.precise) == 1 else ''} (one thread per candidate, {mode} threads per block)" if mode
                       else ("plan_kernel<false,double> (one warp per candidate, FP64)" if int(args.precise) == 1
                             else "plan_kernel<false,float> (one warp per candidate)"))
         peaks = {}
@@ -674,13 +674,16 @@ def main():
                     ms.append(pl.replan_resident()[0].gpu_ms)
                 ex_rows.append({"seed": seed, "cycle_ms": statistics.median(ms), "best_index": int(r1.best_index),
                                 "best_total": float(r1.best_total)})
+            ex_mode = pl.last_sweep_mode()
             ex_med = statistics.median([r["cycle_ms"] for r in ex_rows])
             line["exact_mode"] = {"dtype": "f64", "ms_per_step": ex_med, "value": C / (ex_med * 1e-3), "unit": UNIT,
                                   "max_cycle_ms": max(r["cycle_ms"] for r in ex_rows), "min_cycle_ms": min(r["cycle_ms"] for r in ex_rows),
                                   "seeds_within_50ms": sum(1 for r in ex_rows if r["cycle_ms"] <= 50.0), "seeds": len(ex_rows),
                                   "selection_matches_reference": (all(ex_ok) if ex_ok else None), "per_seed": ex_rows,
-                                  "what": "hmp_set_precision(1): FP64 object loops + FIS for every candidate (plan_kernel<false,double>), "
-                                          "one warp per candidate; resident inputs, CUDA events, median of 2 steps per seed, ms_per_step = median over the seeds"}
+                                  "kernel": (f"sweep_tpc_kernel<double> (one thread per candidate, {ex_mode} threads per block)" if ex_mode
+                                             else "plan_kernel<false,double> (one warp per candidate)"),
+                                  "what": "hmp_set_precision(1): FP64 object loops, literal FIS and scalar section for every candidate; "
+                                          "resident inputs, CUDA events, median of 2 steps per seed, ms_per_step = median over the seeds"}
         except Exception as e:   # the headline line must not depend on it
             line["exact_mode"] = {"error": repr(e)}
     pl.close()

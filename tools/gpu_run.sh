@@ -53,6 +53,17 @@ if [[ "$WHAT" == *" replay "* ]]; then
   python bench.py --cfg cfg4 > $OUT/bench_replay_$TAG.json 2> $OUT/bench_replay_$TAG.err
   tail -c 900 $OUT/bench_replay_$TAG.json; echo
 fi
+if [[ "$WHAT" == *" prof1tpc "* ]]; then   # the exact mode's thread-per-candidate FP64 sweep (r02zz)
+  B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-exact --no-cpu-baseline"
+  ncu --set full --clock-control none --import-source on -k regex:sweep_tpc -s 2 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
+  ncu -i $OUT/${TAG}_full_mode1.ncu-rep --page raw --csv > $OUT/${TAG}_mode1_raw.csv 2>/dev/null
+  python tools/ncu_summary.py $OUT/${TAG}_mode1_raw.csv > $OUT/${TAG}_mode1_ncu_summary.txt
+  ls -la $OUT/${TAG}_full_mode1.ncu-rep
+fi
+if [[ "$WHAT" == *" cfg1 "* ]]; then
+  python bench.py --cfg cfg1 --no-cpu-baseline > $OUT/bench_${TAG}_cfg1.json 2> $OUT/bench_${TAG}_cfg1.err
+  tail -c 400 $OUT/bench_${TAG}_cfg1.json; echo
+fi
 if [[ "$WHAT" == *" prof1 "* ]]; then
   B="python bench.py --precise 1 --steps 1 --seeds 1 --warmup 3 --no-config4 --no-exact --no-cpu-baseline"
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:plan_kernel<\(bool\)0, double, \(bool\)0' -s 2 -c 1 -f -o $OUT/${TAG}_full_mode1 $B > $OUT/ncu_full_mode1_$TAG.log 2>&1
