@@ -19,7 +19,8 @@ from humap_local_planner_b200 import Planner, scenes, config
 from humap_local_planner_b200.capi import HmpEquisampled
 out = {}
 pl = Planner(0)
-for name, seed, lay, mode in (("cfg0", 0, 1, 2), ("cfg0", 1, 2, 2), ("cfg0", 3, 1, 1), ("cfg1", 0, 2, 2), ("cfg1", 1, 1, 0), ("cfg2", 1, 2, 2)):
+for name, seed, lay, mode in (("cfg0", 0, 1, 2), ("cfg0", 1, 2, 2), ("cfg0", 3, 1, 1), ("cfg1", 0, 2, 2), ("cfg1", 1, 1, 0), ("cfg2", 1, 2, 2),
+                             ("cfg1", 2, 2, 1), ("cfg2", 0, 2, 1)):   # ... and the FP64 thread-per-candidate sweep (r02zz)
     cfg = scenes.CONFIGS[name]
     sc = scenes.make_scene(cfg, seed)
     pl.set_precision(mode); pl.set_sweep_layout(lay)
@@ -49,6 +50,14 @@ pl.set_params(scenes.make_params(cfg3)); pl.set_scene(scs[0])
 rb = pl.plan_batch([s.world for s in scs], np.stack([s.cells for s in scs]), [np.stack([s.grids[q] for s in scs]) for q in range(4)],
                    scenes.make_sampling(cfg3), hv_prev=np.array([s.hv_prev for s in scs]))
 out["batch"] = [[r.best_index, r.best_total] for r in rb]
+# the batch once more with its 4 x 4 wave fronts computed on the device (shared-memory wave-front kernel, batched form)
+plans = []
+for q in range(4):
+    xy = [np.asarray(s.plans[q][0], dtype=np.float64).reshape(-1, 2) for s in scs]
+    plans.append((np.concatenate(xy), np.concatenate([[0], np.cumsum([len(a) for a in xy])]).astype(np.int32)))
+pl.compute_mapgrid_batch(np.stack([s.cells for s in scs]), plans, [s_[1] for s_ in scs[0].plans])
+rb2 = pl.plan_batch([s.world for s in scs], None, None, scenes.make_sampling(cfg3), hv_prev=np.array([s.hv_prev for s in scs]))
+out["batch-device-grids"] = [[r.best_index, r.best_total] for r in rb2]
 # the same batch with the second generator of the pool (per-world velocity windows, padded sample lists)
 eq.vth_samples, eq.continued_acceleration = 10, 0
 pl.set_equisampled(eq)
@@ -82,6 +91,7 @@ def test_bounds_checked_build_runs_the_small_cases_cleanly():
     assert r0.returncode == 0, (r0.stdout + r0.stderr)[-2000:]
     plain = json.loads([ln for ln in r0.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     assert checked == plain     # the assertions change nothing: bit-identical results
+    assert checked["batch-device-grids"] == checked["batch"]   # wave fronts on the device == host-computed grids
 
 
 def test_bounds_checked_build_compiles():
