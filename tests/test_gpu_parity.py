@@ -632,6 +632,55 @@ def test_device_wavefront_bit_exact(planner, name, seed):
         assert np.array_equal(got, ref), (k, int((got != ref).sum()))
 
 
+@pytest.mark.parametrize("sx,sy,kind", [(200, 120, "maze"), (97, 213, "noise"), (220, 220, "maze"), (256, 256, "maze"), (64, 48, "open"),
+                                        (200, 200, "walled")])
+def test_device_wavefront_shapes_and_mazes(planner, sx, sy, kind):
+    """The shared-memory wave front (padded grid, claim / resolve, 16-bit cells) on windows that are not square, on
+    mazes whose BFS has > 1000 levels, on a window just below its size limit (220 x 220) and on one above it (256 x 256: the
+    r01 queue kernel takes over), with seeds given twice and seeds on obstacle cells: cell for cell the oracle's queue BFS
+    (base_local_planner::MapGrid::computeTargetDistance, src/map_grid_cost_function.cpp:67-79)."""
+    rng = np.random.default_rng(sx * 1000 + sy)
+    cells = np.zeros((sy, sx), dtype=np.uint8)
+    if kind == "maze":      # serpentine corridors: long shortest paths, small frontiers
+        for r in range(4, sy - 4, 6):
+            cells[r, :] = 254
+            gap = 3 if (r // 6) % 2 == 0 else sx - 6
+            cells[r, gap:gap + 3] = 0
+    elif kind == "noise":   # scattered lethal / inscribed / unknown cells and mid-range costs
+        cells[rng.random((sy, sx)) < 0.25] = 254
+        cells[rng.random((sy, sx)) < 0.05] = 253
+        cells[rng.random((sy, sx)) < 0.03] = 255
+        cells[rng.random((sy, sx)) < 0.10] = 120
+    elif kind == "walled":  # the seeds sit in an enclosure: everything outside stays unreachable
+        cells[60:140, 60] = cells[60:140, 139] = 254
+        cells[60, 60:140] = cells[139, 60:140] = 254
+    res, ox, oy = 0.05, -0.5 * sx * 0.05, -0.5 * sy * 0.05
+    cfg = scenes.CONFIGS["cfg0"]
+    planner.set_precision(2)
+    planner.set_params(scenes.make_params(cfg))
+    planner.set_costmap(cells, ox, oy, res)
+    L = ob.lib()
+    L.orc_mapgrid_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p]
+    L.orc_mapgrid_compute.restype = None
+    line = np.stack([np.linspace(ox + 0.2, ox + sx * res - 0.2, 60), np.full(60, oy + 0.12)], axis=1)
+    twice = np.concatenate([line[:20], line[:20][::-1], line[:5]])          # the plan crosses the same cells again
+    centre = np.array([[0.0, 0.0], [0.02, 0.01]])
+    on_obstacle = np.stack([np.full(30, ox + 0.3), np.linspace(oy + 0.1, oy + sy * res - 0.1, 30)], axis=1)   # crosses the maze walls
+    for k, (plan, local_goal) in enumerate([(line, False), (line, True), (twice, False), (centre, True), (on_obstacle, False),
+                                            (on_obstacle, True)]):
+        plan = np.ascontiguousarray(plan, dtype=np.float64)
+        planner.compute_mapgrid(k % 4, plan, local_goal, 0.0)
+        got = planner.get_mapgrid(k % 4, cells.shape)
+        ref = np.zeros_like(got)
+        L.orc_mapgrid_compute(cells.ctypes.data, sx, sy, ox, oy, res, plan.ctypes.data, plan.shape[0], 1 if local_goal else 0, ref.ctypes.data)
+        assert np.array_equal(got, ref), (kind, k, int((got != ref).sum()))
+        if kind == "maze" and k == 0:
+            n = sx * sy
+            assert ref[ref < n].max() > 1000    # the serpentine really is a long BFS
+    planner.set_precision(False)
+
+
 def test_cycle_with_device_wavefront_equals_uploaded_grids(planner):
     cfg, sc, params, smp = _setup(planner, "cfg1", 3)
     r1, p1 = planner.plan(sc.world, smp)
