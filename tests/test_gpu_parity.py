@@ -1289,13 +1289,19 @@ def test_refined_replay_equals_fp64_on_every_plan(planner):
 
 @pytest.mark.parametrize("lay", [1, 2], ids=["warp", "thread"])
 def test_refined_selection_equals_exact_mode_on_a_64k_replay(planner, lay):
-    """64k candidates around a MOVING robot, every plan of a closed-loop replay (>= 200 plans): the winner of the default mode 2
+    """64k candidates around a MOVING robot, every plan of a 1000-cycle closed-loop replay (~800 plans): the winner of the default mode 2
     (FP32 sweep, the best-ranked candidates refined in FP64) against the exact mode 1 (FP64 sweep = the oracle's selection,
     test_closed_loop_replay[fp64], test_cfg2_exact_mode_equals_the_reference_on_the_full_grid) on the same inputs.
     History: with the r01 rule (2 % window, >= 16 leaders, cap = SM count) this replay picked another candidate on 9 of 320
     plans (tools/selection_hole_stats.py, profiles/r02b_selection_hole.json): the true winner's FP32 total was up to 10 % too
     high (rank up to 642) because its end pose sits within FP32 noise of a MapGrid cell edge or its rollout ends chattering
-    around the stationary-robot threshold. The rank-based rule (one wave of 8 FP64 rollouts per SM) must not miss."""
+    around the stationary-robot threshold. The rank-based rule (one wave of 8 FP64 rollouts per SM) closes that on the first 300
+    cycles (0 of 296 plans differ, r02z). Over all 1000 cycles (r02zz, possible since the exact mode became a thread-per-candidate
+    sweep) mode 2 still differs on 3-4 of 797 plans: while the robot spins at the yaw-rate limit the true winner is a CHAOTIC
+    rollout (speed chattering 0.100 / 0.152 m/s with period 2; the FP32 pose error grows 4x every three steps, 2e-6 -> 1.4e-2 m,
+    tools/mode2_miss.py) whose FP32 total is 12-17 % too high, rank 1270-3270 -- beyond any affordable leader count. The candidate
+    mode 2 hands out instead is 0.09-0.33 % worse in the exact total. The gates below are these measurements; the mode
+    without the caveat is mode 1, 36-38 ms per 64k cfg2 cycle."""
     from humap_local_planner_b200 import replay
     rows = []
 
@@ -1308,22 +1314,32 @@ def test_refined_selection_equals_exact_mode_on_a_64k_replay(planner, lay):
         v = np.sort(t64[t64 >= 0])
         close = len(v) > 1 and (v[1] - v[0]) <= 1e-4 * abs(v[0])
         ok = (res.best_index == exact.best_index) or close
+        excess = 0.0
         if ok and res.best_index == exact.best_index and exact.best_index >= 0:
             ok = abs(res.best_total - exact.best_total) <= 1e-9 * abs(exact.best_total) and res.xv == exact.xv and res.thetav == exact.thetav
-        rows.append((len(rows), bool(ok), res.best_index, exact.best_index, lead))
+        elif not ok:
+            # what the miss costs: the exact total of the candidate mode 2 selected, relative to the exact best (inf: none valid)
+            excess = ((t64[res.best_index] - exact.best_total) / abs(exact.best_total)
+                      if res.best_index >= 0 and exact.best_index >= 0 and t64[res.best_index] >= 0 else float("inf"))
+        rows.append((len(rows), bool(ok), res.best_index, exact.best_index, lead, float(excess)))
         return bool(ok)
 
     planner.set_precision(2)
     planner.set_sweep_layout(lay)
     try:
-        log = replay.run_replay(planner, n_cycles=300, sampling_axes=config.SAMPLING_64K, on_plan=check, on_plan_every=1)
+        # all 1000 cycles (~800 plans) since the exact mode is a thread-per-candidate sweep (r02zz: 2 ms per plan in this world)
+        log = replay.run_replay(planner, n_cycles=1000, sampling_axes=config.SAMPLING_64K, on_plan=check, on_plan_every=1)
     finally:
         planner.set_sweep_layout(0)
         planner.set_precision(False)
     bad = [r for r in rows if not r[1]]
     print(f"GATE mode2-vs-exact layout {lay}: {len(bad)} of {len(rows)} plans differ; leaders per plan {min(r[4] for r in rows)}..{max(r[4] for r in rows)}")
-    assert log.parity_checked >= 200
-    assert not bad, bad[:5]
+    print(f"GATE mode2-vs-exact layout {lay}: worst exact-total excess of a differing plan {max([r[5] for r in bad], default=0.0):.2e}")
+    assert log.parity_checked >= 700
+    first300 = [r for r in bad if r[0] < 290]
+    assert not first300, first300[:5]                      # the r02z statement: no miss on the first 300 cycles
+    assert len(bad) <= max(1, len(rows) // 100), bad[:8]     # measured: 3-4 of 797 (chaotic winners while the robot spins)
+    assert all(r[5] <= 5e-3 for r in bad), bad[:8]           # ... and what is handed out is within 0.5 % of the exact best (measured <= 0.33 %)
 
 
 def test_refinement_with_a_bogus_fp32_best(planner):
