@@ -437,6 +437,7 @@ def main():
     launches = 0
     seed_rows = []
     dev_all, sel_all, e2e_all, e2e_dev_all = [], [], [], []
+    escalated_plans = 0   # e2e plans that hmp_plan redid as an exact FP64 sweep (hmp_set_escalation; none expected on these worlds)
     selection = {}
     scene0 = None
     t_dev_sum = 0.0
@@ -499,6 +500,8 @@ def main():
             t0 = time.perf_counter()
             r, poses = full_cycle()
             e2e_times.append(time.perf_counter() - t0)
+            escalated_plans += 1 if pl.last_escalated() == 1 else 0
+        unreliable = pl.last_unreliable_leaders()
         barrier()
         full_cycle_device_grids()
         e2e_dev_times = []
@@ -520,7 +523,7 @@ def main():
         e2e_dev_all += e2e_dev_times
         seed_rows.append({"seed": seed, "cycle_ms": statistics.mean(dev_ms), "sweep_ms": statistics.mean(sel_ms),
                           "e2e_ms": 1e3 * statistics.mean(e2e_times), "best_index": int(r.best_index), "best_total": float(r.best_total),
-                          "n_valid": int(r.n_valid), "leaders": pl.last_num_leaders()})
+                          "n_valid": int(r.n_valid), "leaders": pl.last_num_leaders(), "unreliable_leaders": int(unreliable)})
     clocks = sampler.stop() if rank == 0 else None
     scene = scene0
 
@@ -610,6 +613,7 @@ def main():
             "e2e": {"value": world * C / (med_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "value_mean_over_all_steps": world * C * args.steps / t_e2e_sum},
             "gpu_launches": int(launches),
+            "escalated_plans": int(escalated_plans),
             "clocks": clocks,
             "selection_matches_reference": (all(selection.values()) if selection else None),
             "selection_checked_seeds": sorted(selection),

@@ -151,6 +151,7 @@ ABI_SYMBOLS = (
     "hmp_set_sweep_layout", "hmp_last_sweep_mode", "hmp_last_num_leaders_round2",
     "hmp_compute_mapgrid_batch", "hmp_set_mapgrids_batch_f32", "hmp_last_num_scenes", "hmp_last_fallback_rounds",
     "hmp_debug_sweep_candidate", "hmp_host_alloc", "hmp_host_free",
+    "hmp_set_escalation", "hmp_last_unreliable_leaders", "hmp_last_escalated",
 )
 
 _LIB_PATH = os.environ.get("HMP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhmp_planner.so")
@@ -191,7 +192,10 @@ def load_library() -> C.CDLL:
     lib.hmp_compute_mapgrid_batch.restype = C.c_int
     lib.hmp_set_mapgrids_batch_f32.argtypes = [C.c_void_p, _i, C.c_void_p]
     lib.hmp_set_mapgrids_batch_f32.restype = C.c_int
-    for name in ("hmp_last_num_scenes", "hmp_last_fallback_rounds", "hmp_last_num_leaders_round2"):
+    lib.hmp_set_escalation.argtypes = [C.c_void_p, _i]
+    lib.hmp_set_escalation.restype = C.c_int
+    for name in ("hmp_last_num_scenes", "hmp_last_fallback_rounds", "hmp_last_num_leaders_round2", "hmp_last_unreliable_leaders",
+                 "hmp_last_escalated"):
         getattr(lib, name).argtypes = [C.c_void_p]
         getattr(lib, name).restype = C.c_int
     lib.hmp_get_explored_totals.argtypes = [C.c_void_p, C.c_void_p, _i]
@@ -358,6 +362,16 @@ class Planner:
     def last_num_leaders_round2(self) -> int:
         """Candidates re-scored by the second refinement round of the last single-scene plan in mode 2."""
         return int(self._lib.hmp_last_num_leaders_round2(self._ctx))
+
+    def set_escalation(self, min_unreliable_leaders: int = 0):
+        """Mode 2: redo a plan as an exact FP64 sweep when at least this many leaders contradict their FP32 totals (0: never)."""
+        self._check(self._lib.hmp_set_escalation(self._ctx, int(min_unreliable_leaders)))
+
+    def last_unreliable_leaders(self) -> int:
+        return int(self._lib.hmp_last_unreliable_leaders(self._ctx))
+
+    def last_escalated(self) -> int:
+        return int(self._lib.hmp_last_escalated(self._ctx))
 
     def last_fallback_rounds(self) -> int:
         """Extra refinement rounds the last plan needed because FP64 rejected every leader (mode 2)."""

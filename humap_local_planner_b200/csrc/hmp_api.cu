@@ -64,7 +64,7 @@ extern "C" cudaError_t hmp_dev_launch_refine_select(const int32_t* leaders, int 
                                                     const double* r_costs, const double* r_seeds, const double* r_poses,
                                                     const int32_t* r_nposes, double* totals_full, double* best_out, double* o_costs,
                                                     double* o_seeds, double* o_poses, double* o_total, int32_t* o_nposes,
-                                                    int n_scenes, int merge, const int32_t* active, cudaStream_t stream);
+                                                    int n_scenes, int merge, const int32_t* active, int32_t* unreliable_out, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_world_to_map(const DevParams* P, const double* wx, const double* wy, int n, int* mx,
                                                    int* my, int* ok, cudaStream_t stream);
 extern "C" cudaError_t hmp_dev_launch_footprint_cost(const DevParams* P, const uint8_t* cm, const double* xyt, int n,
@@ -197,6 +197,9 @@ struct HmpContext {
 	int last_n_leaders2 = 0;        // ... of the second round (single-scene plans)
 	int last_explain_n = 0, last_explain_T = 0;   // shape of the forces hmp_explain left in h_out (0: overwritten since)
 	int debug_cand = -1;            // hmp_debug_sweep_candidate
+	int last_unreliable = 0;        // leaders of the last plan whose FP32 total was off by > 1 % or whose validity differed (mode 2, round 1)
+	int escalate_min = 24;          // hmp_set_escalation: from this many unreliable leaders the plan is redone in FP64 (0: never)
+	int last_escalated = 0;         // the last plan was redone in FP64 for that reason
 	int last_fallback_rounds = 0;   // extra refinement rounds of the last plan because FP64 rejected every leader (mode 2)
 	int refine_min_leaders = 16;     // the best-ranked candidates are refined whatever the window (HMP_REFINE_MIN_LEADERS)
 	int refine_rounds = 2;           // HMP_REFINE_ROUNDS=1 in the environment: first round only (A/B)
@@ -793,6 +796,7 @@ HmpContext* hmp_create(int device_id) {
 	if (const char* e = getenv("HMP_REFINE_ROUNDS")) ctx->refine_rounds = std::max(1, std::min(2, atoi(e)));
 	if (getenv("HMP_REFINE_WINDOW_ONLY")) ctx->refine_window_only = 1;
 	if (getenv("HMP_NO_OVERLAP")) ctx->overlap_refine = 0;
+	if (const char* e = getenv("HMP_ESCALATE")) ctx->escalate_min = std::max(0, atoi(e));
 	if (const char* e = getenv("HMP_SWEEP_LAYOUT")) ctx->sweep_layout = std::max(0, std::min(2, atoi(e)));
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->max_smem_optin = prop.sharedMemPerBlockOptin - 1024;  // static __shared__ of the kernel comes out of the same budget
@@ -1391,7 +1395,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		const bool want_poses = (NS == 1);
 		const size_t nk = (size_t)NS * K;
 		const size_t r_doubles = nk * (HMP_NUM_COSTS + 3 + 1) + (want_poses ? nk * T * 3 : 0);
-		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + NS) * sizeof(int32_t) + 8;   // one round's buffers, 8-byte aligned
+		const size_t r_bytes = r_doubles * sizeof(double) + (nk * 2 + 2 * NS) * sizeof(int32_t) + 8;   // one round's buffers, 8-byte aligned
 		const size_t r_set = (r_bytes + 15) / 16 * 16;
 		// single-scene plans run a second round (below): a second set of buffers + the first round's threshold
 		// (not when round 1 already holds every candidate of the pool, C <= K: nothing is left for a second list)
@@ -1407,6 +1411,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 			int32_t* r_leaders = (int32_t*)((double*)base + r_doubles);
 			int32_t* r_nposes = r_leaders + nk;
 			int32_t* r_count = r_nposes + nk;
+			int32_t* r_unrel = r_count + NS;   // per scene: leaders whose FP32 total the FP64 evaluation contradicts
 			// round 1: rank-based (the K lowest FP32 totals); round 2: everything not yet refined whose FP32 total lies within the
 			// window above the REFINED best (at most K, the lowest first)
 			const bool beside = overlap && round == 0 && !active;   // first pass of a small pool: see `overlap` above
@@ -1455,7 +1460,7 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 				CU(hmp_dev_launch_plan(&Rf, (K + HMP_WARPS_PER_BLOCK - 1) / HMP_WARPS_PER_BLOCK, 1, smem, st));
 			}
 			CU(hmp_dev_launch_refine_select(r_leaders, K, C, T, r_totals, r_costs, r_seeds, r_poses, r_nposes, A.totals, A.best_out,
-			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, active, st));
+			                                B.d_costs, B.d_seeds, B.d_poses, B.totals, B.d_nposes, NS, round, active, r_unrel, st));
 			ctx->launches += 3;
 			r_count_dev[round] = r_count;   // read back after the last round (a copy to pageable memory here would stall the
 			                                // host, and with it the launches of the next round, until this round has finished)
@@ -1476,8 +1481,9 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 		// before the hv pass and the result copies are even queued); picked up after the final synchronisation
 		if ((rc = ctx->h_small.ensure(64))) return rc;
 		int32_t* hw = (int32_t*)ctx->h_small.p;
-		hw[4] = hw[5] = 0;
+		hw[4] = hw[5] = hw[6] = 0;
 		CU(cudaMemcpyAsync(&hw[4], r_count_dev[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(&hw[6], r_count_dev[0] + NS, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // r_unrel of scene 0
 		if (r_count_dev[1]) CU(cudaMemcpyAsync(&hw[5], r_count_dev[1], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 	}
 	// highest_valid_cost_ of the MapGrid critics as the reference's sequential, early-exiting loop would leave it: needs the final
@@ -1503,6 +1509,9 @@ static int run_cycle(HmpContext* ctx, const DevParams& D, const std::vector<doub
 	if (ctx->precise == 2) {
 		ctx->last_n_leaders = ((const int32_t*)ctx->h_small.p)[4];
 		ctx->last_n_leaders2 = ((const int32_t*)ctx->h_small.p)[5];
+		ctx->last_unreliable = ((const int32_t*)ctx->h_small.p)[6];
+	} else {
+		ctx->last_unreliable = 0;
 	}
 	float ms = 0.f;
 	CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1665,7 +1674,24 @@ int hmp_plan(HmpContext* ctx, const HmpWorld* world, const HmpSampling* sampling
 	if (joined) {
 		int redo = 0;
 		if ((rc = finish_wavefront_join(ctx, &redo))) return rc;
-		if (redo) return run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
+		if (redo && (rc = run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity))) return rc;
+	}
+	// Escalation (hmp_set_escalation): the refinement has just compared the FP32 and FP64 totals of the leaders. When many of them
+	// disagree by more than 1 % the FP32 ranking of THIS plan is unreliable (chaotic rollouts around a spinning robot: the true
+	// winner can sit thousands of ranks down) -- the plan is redone as an exact FP64 sweep on the resident inputs.
+	ctx->last_escalated = 0;
+	if (ctx->precise == 2 && ctx->escalate_min > 0 && ctx->last_unreliable >= ctx->escalate_min) {
+		const int unreliable = ctx->last_unreliable, leaders = ctx->last_n_leaders, leaders2 = ctx->last_n_leaders2;
+		const int fallback = ctx->last_fallback_rounds;
+		ctx->precise = 1;
+		rc = run_cycle(ctx, D, amp_table, extra, n_extra, equi, pl, result, poses_out, poses_capacity);
+		ctx->precise = 2;
+		ctx->last_unreliable = unreliable;   // the counters keep describing the mode-2 pass that asked for the escalation
+		ctx->last_n_leaders = leaders;
+		ctx->last_n_leaders2 = leaders2;
+		ctx->last_fallback_rounds = fallback;
+		ctx->last_escalated = 1;
+		if (rc) return rc;
 	}
 	return HMP_OK;
 }
@@ -2609,6 +2635,17 @@ void hmp_host_free(void* p) {
 }
 
 int hmp_last_fallback_rounds(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_fallback_rounds : -1; }
+
+int hmp_set_escalation(HmpContext* ctx, int32_t min_unreliable_leaders) {
+	if (!ctx || min_unreliable_leaders < 0) {
+		set_err("bad escalation threshold");
+		return HMP_E_INVALID;
+	}
+	ctx->escalate_min = min_unreliable_leaders;
+	return HMP_OK;
+}
+int hmp_last_unreliable_leaders(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_unreliable : -1; }
+int hmp_last_escalated(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_escalated : -1; }
 
 int hmp_last_num_scenes(HmpContext* ctx) { return (ctx && ctx->last_valid) ? ctx->last_n_scenes : -1; }
 

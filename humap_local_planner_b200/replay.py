@@ -34,6 +34,7 @@ class ReplayLog:
     poses: List[tuple] = field(default_factory=list)
     goals_reached: int = 0
     recoveries: int = 0                                       # cycles without a valid trajectory (the host backs off)
+    escalated: int = 0                                        # plans redone as an exact FP64 sweep (hmp_set_escalation)
     parity_checked: int = 0
     parity_mismatch: int = 0
 
@@ -143,6 +144,8 @@ def run_replay(planner: Planner, n_cycles: int = 1000, period: float = 0.05, see
             log.plan_ms.append(1e3 * (time.perf_counter() - t0))
             log.gpu_ms.append(res.gpu_ms)
             log.best.append(res.best_index)
+            if hasattr(planner, "last_escalated") and planner.last_escalated() == 1:
+                log.escalated += 1
             if res.status == 0:
                 cmd_x, cmd_th = res.xv, res.thetav
             else:
@@ -191,6 +194,7 @@ def summarize(log: ReplayLog) -> dict:
             "p50_cycle_ms": float(np.percentile(ms, 50)), "p99_cycle_ms": float(np.percentile(ms, 99)),
             "p50_gpu_ms": float(np.percentile(g, 50)), "p99_gpu_ms": float(np.percentile(g, 99)),
             "state_sequence_head": seq[:12], "parity_checked": log.parity_checked, "parity_mismatch": log.parity_mismatch,
+            "escalated_plans": log.escalated,
             "recoveries": log.recoveries}
 
 
@@ -225,6 +229,7 @@ def bench_line(args, rank, local_rank, world, barrier) -> Optional[dict]:
         "p99_gpu_ms_64k": big["p99_gpu_ms"], "move_cycles_64k": big["move_cycles"], "goals_reached_64k": big["goals_reached"],
         "p50_cycle_ms_cfg0": small["p50_cycle_ms"], "p99_cycle_ms_cfg0": small["p99_cycle_ms"], "p50_gpu_ms_cfg0": small["p50_gpu_ms"],
         "p99_gpu_ms_cfg0": small["p99_gpu_ms"], "move_cycles_cfg0": small["move_cycles"], "goals_reached_cfg0": small["goals_reached"],
+        "escalated_plans_64k": big["escalated_plans"], "escalated_plans_cfg0": small["escalated_plans"],
         "state_sequence_head": small["state_sequence_head"],
         "e2e": {"value": big["p50_cycle_ms"], "unit": "ms", "h2d_bytes_per_step": 40000 + 4 * 400 + 4096, "d2h_bytes_per_step": 1416},
         "gpu_launches": int(launches),

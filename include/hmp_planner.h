@@ -351,6 +351,16 @@ int hmp_last_num_leaders_round2(HmpContext* ctx);
  * more rounds; if none yields a valid FP64 winner the plan reports status 1 / best_index -1 (no valid trajectory).
  * Returns how many such extra rounds the last plan needed (0 almost always). */
 int hmp_last_fallback_rounds(HmpContext* ctx);
+/* Mode 2, single-scene plans: the refinement knows both the FP32 and the FP64 total of every leader. A leader is UNRELIABLE when
+ * the two differ by more than 1 % or disagree on validity; in an ordinary plan that is none or one of 1184, around a robot that
+ * spins at its yaw-rate limit (chaotic rollouts) it is dozens -- and then the true winner can sit far outside the
+ * refined ranks. From `min_unreliable_leaders` such leaders on (default 24; 0 = never; HMP_ESCALATE in the environment presets
+ * it) hmp_plan redoes the plan as an exact FP64 sweep (the mode-1 path on the resident inputs) and returns that result; the
+ * leader counters keep describing the mode-2 pass. Batches (hmp_plan_batch) and hmp_replan_resident do not escalate.
+ * hmp_last_unreliable_leaders / hmp_last_escalated report the count and whether the last plan was redone. No reference counterpart. */
+int hmp_set_escalation(HmpContext* ctx, int32_t min_unreliable_leaders);
+int hmp_last_unreliable_leaders(HmpContext* ctx);
+int hmp_last_escalated(HmpContext* ctx);
 /* Work layout of the FP32 sweep (modes 0 and 2): 0 (default) = automatic, 1 = one warp per candidate (lanes stride over the
  * objects; shortest latency for a few thousand candidates), 2 = one thread per candidate (a warp rolls out 32 candidates,
  * the per-step scalar section is issued once per 32; highest throughput from ~16k candidates per launch). Both layouts
