@@ -1384,3 +1384,36 @@ def test_refinement_with_a_bogus_fp32_best(planner):
     assert log.parity_checked >= 50
     assert rows[45][1], rows[45]
     assert log.parity_mismatch == 0, [r for r in rows if not r[1]]
+
+
+def test_escalation_threshold_and_counters(planner):
+    """hmp_set_escalation: the count of unreliable leaders (FP32 total off by > 1 % against the FP64 refinement) is reported,
+    a threshold at that count redoes the plan as an exact FP64 sweep (same result as precision mode 1, the leader counters keep
+    describing the mode-2 pass), a threshold above it does not, 0 disables, a negative one is refused. cfg2 seed 7 is the benchmark
+    world with the most unreliable leaders (8 of 1157)."""
+    from humap_local_planner_b200.capi import HmpError
+    cfg, sc, params, smp = _setup(planner, "cfg2", 7, precise=2)
+    try:
+        planner.set_escalation(0)
+        r0, _ = planner.plan(sc.world, smp, want_poses=False)
+        u, leaders = planner.last_unreliable_leaders(), planner.last_num_leaders()
+        print(f"GATE escalation: cfg2 seed 7 has {u} unreliable leaders of {leaders}")
+        assert planner.last_escalated() == 0 and 1 <= u <= 23 and leaders > 1000   # below the default threshold of 24
+        planner.set_escalation(u + 1)
+        r1, _ = planner.plan(sc.world, smp, want_poses=False)
+        assert planner.last_escalated() == 0 and (r1.best_index, r1.best_total) == (r0.best_index, r0.best_total)
+        planner.set_escalation(u)
+        r2, p2 = planner.plan(sc.world, smp, want_poses=True)
+        assert planner.last_escalated() == 1 and planner.last_unreliable_leaders() == u and planner.last_num_leaders() == leaders
+        t2 = planner.explored_totals(r2.n_candidates)
+        planner.set_precision(1)
+        rx, px = planner.plan(sc.world, smp, want_poses=True)
+        tx = planner.explored_totals(rx.n_candidates)
+        assert (r2.best_index, r2.best_total, r2.xv, r2.thetav, r2.n_valid) == (rx.best_index, rx.best_total, rx.xv, rx.thetav, rx.n_valid)
+        assert np.array_equal(p2, px) and np.array_equal(t2, tx)
+        assert planner.last_escalated() == 0    # mode 1 itself never escalates
+        with pytest.raises(HmpError):
+            planner.set_escalation(-1)
+    finally:
+        planner.set_escalation(24)
+        planner.set_precision(False)
