@@ -680,6 +680,12 @@ int launch_main(HmpContext* ctx, const DevParams& D, const PlanLaunch& pl, int* 
 				tpc_threads = (tpc_threads > 128) ? 128 : 64;
 		}
 	}
+	if (tpc_threads && !f64) {
+		if (const char* e = getenv("HMP_TPC_LAUNCH_THREADS")) {   // A/B: block size of the FP32 thread-per-candidate sweep
+			const int v = atoi(e);
+			if (v >= 32 && v <= hmp_dev_tpc_max_threads() && v % 32 == 0) tpc_threads = v;
+		}
+	}
 	if (tpc_threads && f64) {
 		// finer tickets balance the two rounds a 64k grid takes at 8 warps per SM (rejected candidates end early)
 		const char* e = getenv("HMP_F64_TPC_THREADS");
